@@ -1,0 +1,95 @@
+"""Generate the committed golden fixtures (run in the AUTHORING container only).
+
+    python tests/golden/make_golden.py
+
+* ``stft_rebuild_ref.npz`` -- produced by the UNMODIFIED reference code imported
+  from /root/reference (oracle/ref_import.py shims only np.mat and missing audio
+  libraries): AudioFeature.compute_spectrogram / power_spectrum / divide_phase,
+  DataLoader.padding_batch and AudioReBuild.rebuild_audio.  These pin oracle/stft.py
+  and oracle/rebuild.py.
+* ``frame_counts_ref.npz`` -- T(L) and frame start indices from the reference's
+  en_frame for L in 1..1100 plus the sizes named in SURVEY.md section 8.
+* ``network_oracle.npz`` -- outputs of oracle/network.py (float64) for seeded
+  weights.  NOT produced by the reference (TensorFlow 1.14 is not installable):
+  parity unpinned, see oracle/__init__.py.  Kept so the GPU box can check the CUDA
+  path and the oracle against a value computed elsewhere.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_import, network  # noqa: E402
+from fullycnnspeechenhancement_b200.synth import noisy_utterance  # noqa: E402
+
+
+def main():
+    AudioFeature, AudioReBuild, DataLoader, AudioParser = ref_import.load()
+    af = AudioFeature()
+
+    # ---- frame counts / indices from the reference's en_frame -------------------------
+    lengths = list(range(1, 1101)) + [16000, 24001, 31999, 32000, 32001, 64000]
+    counts, first_start, last_start = [], [], []
+    for L in lengths:
+        _, frames = af.en_frame(0.032, 0.016, 8000, np.arange(1, L + 1, dtype=np.float64))
+        frames = np.asarray(frames)
+        counts.append(frames.shape[0])
+        # frames hold sample_index+1 (0 where zero padded): recover the gather table exactly
+        first_start.append(int(frames[0, 0]) - 1)
+        last_start.append(int(frames[-1, 0]) - 1 if frames[-1, 0] > 0 else -1)
+    np.savez_compressed(os.path.join(HERE, "frame_counts_ref.npz"),
+                        lengths=np.array(lengths, np.int64), counts=np.array(counts, np.int64),
+                        first_start=np.array(first_start, np.int64),
+                        last_start=np.array(last_start, np.int64))
+
+    # ---- STFT + rebuild through the reference ----------------------------------------
+    out = {}
+    cases = [(11, 100), (12, 256), (13, 257), (14, 1000), (15, 2049), (16, 4000)]
+    out["case_seeds"] = np.array([c[0] for c in cases], np.int64)
+    out["case_lengths"] = np.array([c[1] for c in cases], np.int64)
+    specs = []
+    for seed, L in cases:
+        x = noisy_utterance(seed, L)
+        out["wav_%d" % seed] = x
+        X = np.asarray(af.compute_spectrogram(x, 8000, 0.032, 0.016, 256, True))   # [F,T] c128
+        out["spec_%d" % seed] = X
+        out["mag_%d" % seed] = af.power_spectrum(X)
+        out["phase_%d" % seed] = af.divide_phase(X)
+        specs.append(X)
+    # batch layout (data_loader.py:198-209) on the three longest cases
+    pb = DataLoader.padding_batch(None, specs[3:])
+    out["padded_batch"] = pb                                       # [3,Tmax,129,1] c128
+    mag = af.power_spectrum(pb)
+    ph = af.divide_phase(pb)
+    rng = np.random.default_rng(5)
+    # a non-trivial "prediction": magnitude scaled per bin and offset, can go negative
+    pred = (mag.squeeze(-1) * rng.uniform(0.2, 1.2, (1, 1, 129)) - 0.05).astype(np.float32)
+    out["pred"] = pred
+    lens = [c[1] for c in cases[3:]]
+    for nfft in (512, 256):
+        rb = AudioReBuild(nfft=nfft).rebuild_audio(lens, pred, ph.squeeze(-1), 8000, 32.0, 16.0)
+        for i, r in enumerate(rb):
+            out["rebuild%d_%d" % (nfft, i)] = np.asarray(r)
+    np.savez_compressed(os.path.join(HERE, "stft_rebuild_ref.npz"), **out)
+
+    # ---- network oracle outputs -------------------------------------------------------
+    net = {}
+    for arch in ("FullyCNN", "FullyCNNV2", "FullyCNNV3"):
+        w = network.random_weights(arch, seed=1234, randomize_bn=True)
+        net["wsum_" + arch] = np.array([float(np.sum([np.sum(v.astype(np.float64)) for v in w.values()])),
+                                        float(np.sum([np.sum(np.abs(v.astype(np.float64))) for v in w.values()]))])
+        rng = np.random.default_rng(77)
+        for T in (1, 7, 8, 9, 12):
+            x = np.abs(rng.normal(0, 3.0, (2, T, 129, 1))).astype(np.float32)
+            net["x_%s_%d" % (arch, T)] = x
+            net["y_%s_%d" % (arch, T)] = network.forward(arch, w, x, np.float64)
+    np.savez_compressed(os.path.join(HERE, "network_oracle.npz"), **net)
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
