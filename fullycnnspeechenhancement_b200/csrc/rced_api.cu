@@ -1,0 +1,447 @@
+// C ABI of librced_b200.so (declared in include/rced.h) plus the small helper kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/rced.h"
+#include "rced_arch.cuh"
+#include "rced_internal.h"
+
+namespace rced {
+
+static thread_local std::string t_err;
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int fail(int code, const std::string& msg) {
+    t_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(RCED_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+// ---- FP32 FFMA peak microbenchmark -------------------------------------------------------
+constexpr int kPeakChains = 16;
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+    float acc[kPeakChains];
+#pragma unroll
+    for (int i = 0; i < kPeakChains; ++i) acc[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < kPeakChains; ++i) acc[i] = fmaf(acc[i], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPeakChains; ++i) s += acc[i];
+    if (s == 12345.678f) out[0] = s;   // never true in practice; keeps the chains alive
+}
+
+cudaError_t run_ffma_peak(int iters, int num_sms, double* tflops) {
+    float* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4);
+    if (e != cudaSuccess) return e;
+    const int ctas = num_sms * 8;   // 8 CTAs x 256 threads = 64 warps per SM
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(t0);
+        ffma_peak_kernel<<<ctas, 256>>>(d, iters, 0.999f, 0.001f);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        count_launch();
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        const double flops = 2.0 * (double)ctas * 256.0 * (double)iters * 8.0 * kPeakChains;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;   // first repetition is warm-up
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d);
+    *tflops = best;
+    return e;
+}
+
+// ---- element-wise magnitude / unit phase of a complex spectrogram ----------------------------
+__global__ void mag_phase_kernel(const float2* __restrict__ x, long long n, float* __restrict__ mag, float2* __restrict__ ph) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = x[i];
+        const float m = sqrtf(fmaf(v.x, v.x, v.y * v.y));
+        if (mag) mag[i] = m;
+        if (ph) ph[i] = m > 0.f ? make_float2(v.x / m, v.y / m) : make_float2(1.f, 0.f);
+    }
+}
+
+// ---- tensor-memory round trip (same tcgen05.st/ld shapes as the network kernel) --------------
+__global__ void __launch_bounds__(128) tmem_selftest_kernel(int* mismatches) {
+    __shared__ uint32_t s_tmem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&s_tmem))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t base = s_tmem + ((uint32_t)(warp & 3) << 21);
+    int bad = 0;
+    for (int col = 0; col < 508; col += 4) {
+        const float v0 = (float)(threadIdx.x * 1000 + col), v1 = v0 + 1.f, v2 = v0 + 2.f, v3 = v0 + 3.f;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + col), "f"(v0),
+                     "f"(v1), "f"(v2), "f"(v3)
+                     : "memory");
+    }
+    {
+        const float v = (float)(threadIdx.x * 1000 + 511);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(base + 511), "f"(v) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    __syncwarp();
+    for (int col = 0; col < 508; col += 4) {
+        float r0, r1, r2, r3;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3)
+                     : "r"(base + col)
+                     : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("" : "+f"(r0), "+f"(r1), "+f"(r2), "+f"(r3)::"memory");
+        const float v0 = (float)(threadIdx.x * 1000 + col);
+        bad += (r0 != v0) + (r1 != v0 + 1.f) + (r2 != v0 + 2.f) + (r3 != v0 + 3.f);
+    }
+    {
+        float r;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(r) : "r"(base + 511) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("" : "+f"(r)::"memory");
+        bad += (r != (float)(threadIdx.x * 1000 + 511));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(s_tmem) : "memory");
+    (void)lane;
+}
+
+cudaError_t run_tmem_selftest(int* mismatches) {
+    int* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(int));
+    if (e != cudaSuccess) return e;
+    cudaMemset(d, 0, sizeof(int));
+    tmem_selftest_kernel<<<4, 128>>>(d);
+    count_launch();
+    e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches, d, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e;
+}
+
+// ---- host-side packing of the folded weights into the shared-memory image -------------------
+static void pack_weights(int arch, const float* folded, float* packed) {
+    const int nl = num_layers(arch);
+    memset(packed, 0, sizeof(float) * (size_t)pad4(packed_count(arch)));
+    for (int i = 0; i < nl; ++i) {
+        const LSpec s = spec(arch, i);
+        const float* k = folded + folded_off(arch, i);                          // [kh][kw][cin][cout]
+        const float* b = k + (size_t)s.kh * s.kw * s.cin * s.cout;
+        float* w = packed + packed_w_off(arch, i);
+        float* pb = packed + packed_b_off(arch, i);
+        if (i == nl - 1) {   // (1,129) layer, cout == 1: W[cin][132]
+            for (int c = 0; c < s.cin; ++c)
+                for (int t = 0; t < s.kw; ++t) w[c * kFinalKP + t] = k[((size_t)t * s.cin + c) * s.cout];
+            pb[0] = b[0];
+        } else {
+            const int ce = cin_eff(arch, i), cp = pad4(s.cout);
+            for (int c = 0; c < ce; ++c)
+                for (int t = 0; t < s.kw; ++t)
+                    for (int o = 0; o < s.cout; ++o) {
+                        // first layer: "channel" c is the time tap (kh index), cin == 1
+                        const size_t src = i == 0 ? (((size_t)c * s.kw + t) * s.cin + 0) * s.cout + o
+                                                  : (((size_t)0 * s.kw + t) * s.cin + c) * s.cout + o;
+                        w[((size_t)c * s.kw + t) * cp + o] = k[src];
+                    }
+            for (int o = 0; o < s.cout; ++o) pb[o] = b[o];
+        }
+    }
+}
+
+}  // namespace rced
+
+using namespace rced;
+
+struct rced_handle {
+    int arch;
+    int device;
+    int num_sms;
+    bool skip_in_tmem;
+    float* d_packed;
+    float* d_scratch;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+extern "C" {
+
+int rced_abi_version(void) { return 1; }
+const char* rced_last_error(void) { return t_err.c_str(); }
+
+int64_t rced_num_frames(int64_t n) {
+    const int64_t d = n >= RCED_FRAME_LEN ? n - RCED_FRAME_LEN : RCED_FRAME_LEN - n;
+    return (d + RCED_FRAME_HOP - 1) / RCED_FRAME_HOP + 1;
+}
+
+static bool arch_ok(int a) { return a >= 1 && a <= 3; }
+
+int64_t rced_folded_weight_count(int arch) { return arch_ok(arch) ? folded_count(arch) : -1; }
+int rced_num_layers(int arch) { return arch_ok(arch) ? num_layers(arch) : -1; }
+int rced_layer_shape(int arch, int layer, int* kh, int* kw, int* cin, int* cout) {
+    if (!arch_ok(arch) || layer < 0 || layer >= num_layers(arch)) return fail(RCED_ERR_ARG, "bad arch/layer");
+    const LSpec s = spec(arch, layer);
+    if (kh) *kh = s.kh;
+    if (kw) *kw = s.kw;
+    if (cin) *cin = s.cin;
+    if (cout) *cout = s.cout;
+    return RCED_OK;
+}
+int64_t rced_packed_weight_count(int arch) { return arch_ok(arch) ? pad4(packed_count(arch)) : -1; }
+int rced_pack_weights(int arch, const float* folded, size_t n_folded, float* packed, size_t n_packed) {
+    if (!arch_ok(arch)) return fail(RCED_ERR_ARG, "unknown arch");
+    if (!folded || !packed) return fail(RCED_ERR_ARG, "null pointer");
+    if ((int64_t)n_folded != folded_count(arch)) return fail(RCED_ERR_ARG, "folded weight count mismatch");
+    if ((int64_t)n_packed != pad4(packed_count(arch))) return fail(RCED_ERR_ARG, "packed weight count mismatch");
+    pack_weights(arch, folded, packed);
+    return RCED_OK;
+}
+int rced_debug_layout(int arch, int64_t* out, int n) {
+    if (!arch_ok(arch) || !out || n < 8 + 4 * num_layers(arch)) return fail(RCED_ERR_ARG, "bad argument");
+    out[0] = stage_row(arch);
+    out[1] = slot_floats(arch);
+    out[2] = wide_floats(arch);
+    out[3] = (int64_t)net_smem_bytes_rt(arch);
+    out[4] = skip_total_cols(arch);
+    out[5] = out[6] = out[7] = 0;
+    for (int i = 0; i < num_layers(arch); ++i) {
+        const LSpec s = spec(arch, i);
+        out[8 + 4 * i] = packed_w_off(arch, i);
+        out[9 + 4 * i] = packed_b_off(arch, i);
+        out[10 + 4 * i] = s.save >= 0 ? skip_col_base(arch, s.save) : -1;
+        out[11 + 4 * i] = s.add >= 0 ? skip_col_base(arch, s.add) : -1;
+    }
+    return RCED_OK;
+}
+
+int64_t rced_mac_per_frame(int arch, int valid_only) { return arch_ok(arch) ? mac_per_frame(arch, valid_only != 0) : -1; }
+
+int rced_create(int arch, const float* folded, size_t n_folded, int device, rced_handle** out) {
+    if (!out) return fail(RCED_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (!arch_ok(arch)) return fail(RCED_ERR_ARG, "unknown arch (1=FullyCNN, 2=FullyCNNV2, 3=FullyCNNV3)");
+    if (!folded || (int64_t)n_folded != folded_count(arch))
+        return fail(RCED_ERR_ARG, "folded weight count mismatch: expected " + std::to_string(folded_count(arch)) + ", got " +
+                                      std::to_string(n_folded));
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(RCED_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(RCED_ERR_ARG, "bad device index");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RCED_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(RCED_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                       "; this library is built for sm_100a (B200) only");
+    if ((e = upload_tables_stft()) != cudaSuccess) return cuda_fail(e, "upload_tables_stft");
+    if ((e = upload_tables_istft()) != cudaSuccess) return cuda_fail(e, "upload_tables_istft");
+
+    std::vector<float> packed((size_t)pad4(packed_count(arch)));
+    pack_weights(arch, folded, packed.data());
+    rced_handle* h = new rced_handle();
+    h->arch = arch;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->skip_in_tmem = true;
+    h->d_packed = nullptr;
+    h->d_scratch = nullptr;
+    if ((e = cudaMalloc(&h->d_packed, packed.size() * sizeof(float))) != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaMalloc(weights)");
+    }
+    if ((e = cudaMemcpy(h->d_packed, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cudaFree(h->d_packed);
+        delete h;
+        return cuda_fail(e, "cudaMemcpy(weights)");
+    }
+    *out = h;
+    return RCED_OK;
+}
+
+void rced_destroy(rced_handle* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    if (h->d_packed) cudaFree(h->d_packed);
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    delete h;
+}
+
+int rced_arch(const rced_handle* h) { return h ? h->arch : -1; }
+int rced_device(const rced_handle* h) { return h ? h->device : -1; }
+
+int rced_set_skip_in_tmem(rced_handle* h, int enable) {
+    if (!h) return fail(RCED_ERR_ARG, "null handle");
+    if (!enable && !h->d_scratch) {
+        DeviceGuard guard(h->device);
+        const size_t bytes = (size_t)h->num_sms * kWarpsPerCta * 512 * 32 * sizeof(float);
+        cudaError_t e = cudaMalloc(&h->d_scratch, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(skip scratch)");
+    }
+    h->skip_in_tmem = enable != 0;
+    return RCED_OK;
+}
+
+int rced_stft(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, const int64_t* row_off,
+              int n_utt, int64_t total_rows, float* mag, float* phase, void* stream) {
+    if (!h) return fail(RCED_ERR_ARG, "null handle");
+    if (n_utt < 0 || total_rows < 0) return fail(RCED_ERR_ARG, "negative size");
+    if (n_utt == 0 || total_rows == 0) return RCED_OK;
+    if (!wav || !wav_off || !wav_len || !row_off || !mag) return fail(RCED_ERR_ARG, "null pointer");
+    DeviceGuard guard(h->device);
+    StftParams p;
+    p.wav = wav;
+    p.wav_off = reinterpret_cast<const long long*>(wav_off);
+    p.wav_len = wav_len;
+    p.row_off = reinterpret_cast<const long long*>(row_off);
+    p.n_utt = n_utt;
+    p.total_rows = total_rows;
+    p.mag = mag;
+    p.phase = reinterpret_cast<float2*>(phase);
+    cudaError_t e = launch_stft(p, (cudaStream_t)stream);
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_stft launch");
+}
+
+int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n_utt, int64_t total_rows, float* pred,
+                 void* stream) {
+    if (!h) return fail(RCED_ERR_ARG, "null handle");
+    if (n_utt < 0 || total_rows < 0) return fail(RCED_ERR_ARG, "negative size");
+    if (n_utt == 0 || total_rows == 0) return RCED_OK;
+    if (!mag || !row_off || !pred) return fail(RCED_ERR_ARG, "null pointer");
+    if (mag == pred) return fail(RCED_ERR_ARG, "mag and pred must not alias");
+    DeviceGuard guard(h->device);
+    NetParams p;
+    p.packed = h->d_packed;
+    p.in = mag;
+    p.out = pred;
+    p.row_off = reinterpret_cast<const long long*>(row_off);
+    p.n_utt = n_utt;
+    p.total_rows = total_rows;
+    p.skip_scratch = h->d_scratch;
+    cudaError_t e = launch_net(h->arch, h->skip_in_tmem, p, h->num_sms, (cudaStream_t)stream);
+    count_launch();
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_forward launch");
+}
+
+int rced_istft(rced_handle* h, const float* pred, const float* phase, const int64_t* row_off, int n_utt,
+               int64_t max_rows_per_utt, int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len,
+               void* stream) {
+    if (!h) return fail(RCED_ERR_ARG, "null handle");
+    if (irfft_n != 512 && irfft_n != 256) return fail(RCED_ERR_ARG, "irfft_n must be 512 or 256");
+    if (n_utt < 0 || max_rows_per_utt < 0) return fail(RCED_ERR_ARG, "negative size");
+    if (n_utt == 0 || max_rows_per_utt == 0) return RCED_OK;
+    if (!pred || !phase || !row_off || !out || !out_off || !out_len) return fail(RCED_ERR_ARG, "null pointer");
+    DeviceGuard guard(h->device);
+    IstftParams p;
+    p.pred = pred;
+    p.phase = reinterpret_cast<const float2*>(phase);
+    p.row_off = reinterpret_cast<const long long*>(row_off);
+    p.n_utt = n_utt;
+    p.irfft_n = irfft_n;
+    long long chunk = 64;
+    while ((max_rows_per_utt + 1 + chunk - 1) / chunk > 65535) chunk *= 2;
+    p.chunk_segs = (int)chunk;
+    p.out = out;
+    p.out_off = reinterpret_cast<const long long*>(out_off);
+    p.out_len = out_len;
+    cudaError_t e = launch_istft(p, max_rows_per_utt, (cudaStream_t)stream);
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_istft launch");
+}
+
+int rced_enhance(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, const int64_t* row_off,
+                 int n_utt, int64_t total_rows, int64_t max_rows_per_utt, int irfft_n, float* ws_mag, float* ws_phase,
+                 float* ws_pred, float* out, const int64_t* out_off, const int32_t* out_len, void* stream) {
+    if (!ws_mag || !ws_phase || !ws_pred) return fail(RCED_ERR_ARG, "null workspace");
+    int r = rced_stft(h, wav, wav_off, wav_len, row_off, n_utt, total_rows, ws_mag, ws_phase, stream);
+    if (r != RCED_OK) return r;
+    r = rced_forward(h, ws_mag, row_off, n_utt, total_rows, ws_pred, stream);
+    if (r != RCED_OK) return r;
+    return rced_istft(h, ws_pred, ws_phase, row_off, n_utt, max_rows_per_utt, irfft_n, out, out_off, out_len, stream);
+}
+
+int rced_mag_phase(int device, const float* X, int64_t n, float* mag, float* phase, void* stream) {
+    if (n < 0) return fail(RCED_ERR_ARG, "negative size");
+    if (n == 0) return RCED_OK;
+    if (!X) return fail(RCED_ERR_ARG, "null pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(RCED_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    DeviceGuard guard(device);
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    mag_phase_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(X), n, mag,
+                                                                         reinterpret_cast<float2*>(phase));
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_mag_phase launch");
+}
+
+int rced_ffma_peak(int device, int iters, double* tflops) {
+    if (!tflops || iters <= 0) return fail(RCED_ERR_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(RCED_ERR_CUDA, "no such CUDA device");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    e = run_ffma_peak(iters, prop.multiProcessorCount, tflops);
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "ffma peak");
+}
+
+int rced_selftest_tmem(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(RCED_ERR_CUDA, "no such CUDA device");
+    DeviceGuard guard(device);
+    int bad = -1;
+    cudaError_t e = run_tmem_selftest(&bad);
+    if (e != cudaSuccess) return cuda_fail(e, "tmem selftest");
+    if (bad != 0) return fail(RCED_ERR_STATE, "tensor memory round trip: " + std::to_string(bad) + " mismatches");
+    return RCED_OK;
+}
+
+int64_t rced_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Warp-level 128-point complex FFT shared by the STFT (K1) and iSTFT (K3) kernels.
+//
+// One warp transforms one 128-point sequence held 4 values per lane: a radix-4 butterfly in
+// registers, a twiddle, then a 32-point decimation-in-frequency FFT across the lanes made of
+// five shfl_xor stages.  tools/fft_emulator.py is the numpy lane-by-lane model of this file.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace rced {
+
+// tables filled by upload_tables() (rced_tables.cu), copied to shared memory by the kernels
+struct FftTables {
+    float2 tw256[256];     // e^{-2 pi i j / 256}
+    float2 tw512[132];     // e^{+ pi i k / 256}, k = 0..128 (pre-twiddle of the odd output samples)
+    float ham[256];        // np.hamming(256)
+    float inv_ham[256];    // 1 / np.hamming(256)
+};
+// one copy per translation unit (no relocatable device code needed); each TU that uses the
+// tables exports an upload function built on upload_tables_local()
+static __device__ FftTables g_tables;
+
+static inline cudaError_t upload_tables_local() {
+    static FftTables host;   // ~5 KB, filled in double precision
+    const double pi = 3.14159265358979323846;
+    for (int j = 0; j < 256; ++j) {
+        host.tw256[j] = make_float2((float)cos(2.0 * pi * j / 256.0), (float)(-sin(2.0 * pi * j / 256.0)));
+        const double w = 0.54 - 0.46 * cos(2.0 * pi * j / 255.0);   // np.hamming(256), symmetric
+        host.ham[j] = (float)w;
+        host.inv_ham[j] = (float)(1.0 / w);
+    }
+    for (int k = 0; k < 132; ++k) {
+        const int kk = k > 128 ? 128 : k;
+        host.tw512[k] = make_float2((float)cos(pi * kk / 256.0), (float)sin(pi * kk / 256.0));
+    }
+    return cudaMemcpyToSymbol(g_tables, &host, sizeof(FftTables));
+}
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ float2 shfl_xor2(float2 a, int m) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, a.x, m), __shfl_xor_sync(0xffffffffu, a.y, m));
+}
+
+// In : v[a] = z[lane + 32 a]                       (natural order)
+// Out: v[b] = Z[4 * bitrev5(lane) + b]             (INV: unscaled inverse transform)
+template <bool INV>
+__device__ __forceinline__ void fft128_warp(float2 (&v)[4], const int lane, const float2* __restrict__ tw256) {
+    const float2 s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]);
+    const float2 s2 = cadd(v[1], v[3]), s3 = csub(v[1], v[3]);
+    // forward: -i*s3 = (s3.y, -s3.x); inverse: +i*s3 = (-s3.y, s3.x)
+    const float2 r3 = INV ? make_float2(-s3.y, s3.x) : make_float2(s3.y, -s3.x);
+    v[0] = cadd(s0, s2);
+    v[1] = cadd(s1, r3);
+    v[2] = csub(s0, s2);
+    v[3] = csub(s1, r3);
+#pragma unroll
+    for (int b = 1; b < 4; ++b) {
+        float2 w = tw256[2 * lane * b];   // <= 186
+        if (INV) w.y = -w.y;
+        v[b] = cmul(v[b], w);
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        float2 w = tw256[(lane & (s - 1)) * (128 / s)];
+        if (INV) w.y = -w.y;
+        const bool hi = (lane & s) != 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float2 o = shfl_xor2(v[b], s);
+            v[b] = hi ? cmul(csub(o, v[b]), w) : cadd(v[b], o);
+        }
+    }
+}
+
+__device__ __forceinline__ int bitrev5(int lane) { return (int)(__brev((unsigned)lane) >> 27); }
+
+}  // namespace rced
