@@ -1,0 +1,102 @@
+"""AudioReBuild and the scoring helpers with the reference's interface
+(model_utils/utils.py of the reference).  rebuild_audio runs the reconstruction kernel (K3)."""
+import numpy as np
+import torch
+
+from .. import runtime
+
+
+class AverageMeter(object):
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = 0
+        self.avg = 0
+        self.sum = 0
+        self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+class SDR(object):
+    """10*log10(||ref||^2 / ||est - ref||^2) (utils.py:68-90 of the reference)."""
+
+    def sdr(self, ref, est):
+        assert len(ref) == len(est)
+        ref = np.asarray(ref, dtype=np.float64)
+        est = np.asarray(est, dtype=np.float64)
+        return 10 * np.log10(np.sum(ref ** 2) / np.sum((est - ref) ** 2))
+
+    def __call__(self, x, y):
+        return self.sdr(x, y)
+
+
+class _Unavailable(object):
+    def __init__(self, name, sr=8000):
+        self.name = name
+
+    def __call__(self, x, y):
+        raise ImportError("%s scoring needs the third-party package used by the reference, which is not "
+                          "installed; it is outside the enhancement forward path" % self.name)
+
+
+class PESQ(_Unavailable):
+    def __init__(self, sr=8000):
+        super(PESQ, self).__init__("PESQ (pypesq)", sr)
+
+
+class STOI(_Unavailable):
+    def __init__(self, sr=8000):
+        super(STOI, self).__init__("STOI (pystoi)", sr)
+
+
+class AudioReBuild(object):
+    def __init__(self, windows_name=None, nfft=512, device=None):
+        if windows_name not in (None, "hamming"):
+            raise NotImplementedError("only the Hamming window has a CUDA path")
+        if nfft not in (512, 256):
+            raise NotImplementedError("irfft length must be 512 (the reference's default) or 256")
+        self.nfft = nfft
+        self.device_index = runtime.default_device() if device is None else int(device)
+        self._eng = None
+
+    def _engine(self):
+        if self._eng is None:
+            from .. import _lib
+            from ..engine import Enhancer
+            n = _lib.lib().rced_folded_weight_count(2)
+            self._eng = Enhancer("FullyCNNV2", np.zeros(n, np.float32), device=self.device_index)
+        return self._eng
+
+    def rebuild_audio(self, sig_length_list, spec, phase, sample_rate, windows_ms, stride_ms):
+        """spec [N,T,F] real, phase [N,T,F] complex -> list of N float64 arrays truncated to
+        sig_length_list (utils.py:171-183 of the reference)."""
+        n_window = int((windows_ms * sample_rate) / 1000)
+        n_stride = int((stride_ms * sample_rate) / 1000)
+        if (n_window, n_stride) != (256, 128):
+            raise NotImplementedError("the CUDA reconstruction implements 256-sample frames with a 128-sample hop")
+        spec = np.asarray(spec)
+        phase = np.asarray(phase)
+        if spec.ndim != 3 or spec.shape[2] != 129 or phase.shape != spec.shape:
+            raise ValueError("spec and phase must both be [N, T, 129]")
+        N, T = spec.shape[0], spec.shape[1]
+        lens = np.asarray(sig_length_list, dtype=np.int64)
+        assert len(lens) == N
+        keep = np.minimum(lens, (T + 1) * 128)            # numpy slicing [:L] never extends
+        eng = self._engine()
+        dev = eng.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        ph = np.stack([phase.real, phase.imag], axis=-1).astype(np.float32).reshape(N * T, 129, 2)
+        out_off = np.concatenate([[0], np.cumsum(keep)[:-1]]).astype(np.int64)
+        out = torch.zeros(int(keep.sum()) + 1, dtype=torch.float32, device=dev)
+        eng.istft_device(t(spec.astype(np.float32).reshape(N * T, 129)), t(ph),
+                         torch.arange(N + 1, dtype=torch.int64, device=dev) * T, T, out, t(out_off),
+                         t(keep.astype(np.int32)), irfft_n=self.nfft)
+        torch.cuda.synchronize(dev)
+        o = out.cpu().numpy().astype(np.float64)
+        return [o[out_off[i]:out_off[i] + keep[i]] for i in range(N)]

@@ -1,0 +1,142 @@
+"""GPU: the reference-shaped classes (config -> model construction -> checkpoint restore ->
+test_step / denoise / test) drive the CUDA path and agree with the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from fullycnnspeechenhancement_b200 import audio_io                      # noqa: E402
+from fullycnnspeechenhancement_b200.config import load_conf_info         # noqa: E402
+from fullycnnspeechenhancement_b200.data_utils.data_loader import AudioParser, DataLoader, DataSet  # noqa: E402
+from fullycnnspeechenhancement_b200.model_utils import ckpt              # noqa: E402
+from fullycnnspeechenhancement_b200.model_utils.model import FullyCNNSEModelV3  # noqa: E402
+from fullycnnspeechenhancement_b200.model_utils.tester import FullyCNNTester    # noqa: E402
+from fullycnnspeechenhancement_b200.model_utils.utils import AudioReBuild       # noqa: E402
+from fullycnnspeechenhancement_b200.synth import noisy_utterance         # noqa: E402
+from oracle import network, rebuild, stft                                # noqa: E402
+
+
+def _write_cfg(path, section, ckpt_path, net_work, save, manifest=None):
+    lines = ["[%s]" % section, "batch_size=2", "checkpoint_filepath=%s" % ckpt_path, "", "[model]", "net_arch=RCED",
+             "net_work=%s" % net_work, "", "[data]", "snr=0", "sample_rate=8000", "nfft=256", "feature_dim=129",
+             "window_ms=32", "stride_ms=16", "windows=hanning", "audio_save_path=%s" % save]
+    if manifest:
+        lines.append("test_manifest_path=%s" % manifest)
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("dropin")
+    w = network.random_weights("FullyCNNV2", seed=11, randomize_bn=True)
+    prefix = str(d / "ckpt" / "RCED_FullyCNNV2_0_9.ckpt")
+    ckpt.write_checkpoint(prefix, w)
+    wavs = []
+    for i, L in enumerate([16000, 12345, 8000]):
+        p = str(d / ("utt%d.wav" % i))
+        audio_io.write_wav(p, noisy_utterance(70 + i, L), 8000)
+        wavs.append(p)
+    manifest = str(d / "manifest.dev")
+    with open(manifest, "w") as f:
+        for p, L in zip(wavs, [16000, 12345, 8000]):
+            f.write(json.dumps({"audio_filepath": p, "duration": L / 8000.0}) + "\n")
+    return dict(dir=d, weights=w, prefix=prefix, wavs=wavs, manifest=manifest)
+
+
+def test_parser_extractor_rebuilder_match_oracle():
+    parser = AudioParser(8000, 32, 16, use_complex=True)
+    x = noisy_utterance(5, 9000)
+    spec = parser.parse_audio(x)                                   # [129, T] complex128
+    ref = stft.compute_spectrogram(x, 8000, 0.032, 0.016, 256, True)
+    assert spec.shape == ref.shape and spec.dtype == np.complex128
+    assert np.abs(spec - ref).max() / np.abs(ref).max() <= 1e-4
+    mag = parser.extractor.power_spectrum(ref)
+    ph = parser.extractor.divide_phase(ref)
+    assert np.abs(mag - stft.power_spectrum(ref)).max() / np.abs(ref).max() <= 1e-6
+    assert np.abs(ph - stft.divide_phase(ref)).max() <= 1e-5
+    z = parser.extractor.divide_phase(np.zeros((2, 3), np.complex128))
+    assert np.all(z == 1 + 0j)
+    with pytest.raises(ValueError):                                # audio_feature.py:29-30
+        parser.extractor.compute_spectrogram(x, 8000, 0.016, 0.032, 256)
+    # reconstruction of a batch with the reference call signature
+    X = stft.padding_batch([ref, stft.compute_spectrogram(x[:4000], 8000, 0.032, 0.016, 256, True)])
+    spec3 = (stft.power_spectrum(X).squeeze(-1) * 0.7).astype(np.float32)
+    ph3 = stft.divide_phase(X).squeeze(-1)
+    for nfft in (512, 256):
+        got = AudioReBuild(nfft=nfft).rebuild_audio([9000, 4000], spec3, ph3, 8000, 32.0, 16.0)
+        want = rebuild.rebuild_audio([9000, 4000], spec3, ph3, 8000, 32.0, 16.0, nfft=nfft)
+        for g, w_ in zip(got, want):
+            assert g.dtype == np.float64 and len(g) == len(w_)
+            assert rebuild.sdr_db(w_, g) >= 60.0
+
+
+def test_tester_from_config_and_checkpoint(workdir, capsys):
+    cfg_path = str(workdir["dir"] / "test.cfg")
+    _write_cfg(cfg_path, "testing", workdir["prefix"], "FullyCNNV2", str(workdir["dir"] / "out_test"), workdir["manifest"])
+    cfg = load_conf_info(cfg_path)
+    tester = FullyCNNTester(cfg)
+    assert "Total number of Parameters: 32192" in capsys.readouterr().out      # readme.md:66
+    x = np.abs(np.random.default_rng(0).normal(0, 2, (2, 20, 129, 1)))          # float64 feed, like the reference
+    y = tester.test_step(x)
+    assert y.shape == (2, 20, 129, 1) and y.dtype == np.float32
+    ref = network.forward("FullyCNNV2", workdir["weights"], x.astype(np.float32), np.float64)
+    assert np.abs(y - ref).max() / np.abs(ref).max() <= 1e-4
+    # the whole evaluation loop (test.py main)
+    ds = DataSet(workdir["manifest"], None, sample_rate=8000, window_ms=32, stride_ms=16, use_complex=True)
+    loader = DataLoader(ds, 2, sampler=None, num_works=1)
+    tester.test(loader)
+    out_dir = str(workdir["dir"] / "out_test")
+    assert sorted(os.listdir(out_dir)) == sorted(
+        [n for i in range(3) for n in ("utt%d.wav" % i, "utt%d_mix.wav" % i, "utt%d_de.wav" % i)])
+    de, _ = audio_io.load_wav(os.path.join(out_dir, "utt1_de.wav"), 8000)
+    assert len(de) == 12345
+
+
+def test_inference_engine_reshape_quirk_and_transpose(workdir):
+    from fullycnnspeechenhancement_b200.infer import InferenceEngine
+    cfg_path = str(workdir["dir"] / "infer.cfg")
+    _write_cfg(cfg_path, "inference", workdir["prefix"], "FullyCNNV2", str(workdir["dir"] / "out_infer"))
+    eng = InferenceEngine(load_conf_info(cfg_path))                  # [inference] section accepted
+    sig, _ = audio_io.load_wav(workdir["wavs"][0], 8000)
+    out = eng.enhance_signal(sig)
+    # oracle of infer.py:54-71 including the reshape (not transpose) of the [F,T] arrays
+    X = stft.compute_spectrogram(sig, 8000, 0.032, 0.016, 256, True)
+    mag = np.reshape(stft.power_spectrum(X), (1, X.shape[1], X.shape[0], 1))
+    ph = np.reshape(stft.divide_phase(X), (1, X.shape[1], X.shape[0]))
+    pred = network.forward("FullyCNNV2", workdir["weights"], mag.astype(np.float32), np.float64).astype(np.float32)
+    ref = rebuild.rebuild_audio([len(sig)], pred.squeeze(-1), ph, 8000, 32, 16)[0]
+    assert len(out) == len(sig) and rebuild.sdr_db(ref, out) >= 60.0
+    path = eng.denoise(workdir["wavs"][0])
+    assert path.endswith("utt0_de.wav") and os.path.exists(path)
+    # the layout test.py uses
+    eng.layout = "transpose"
+    out_t = eng.enhance_signal(sig)
+    Xt = np.transpose(X)[None, :, :, None]
+    pred_t = network.forward("FullyCNNV2", workdir["weights"], stft.power_spectrum(Xt).astype(np.float32), np.float64)
+    ref_t = rebuild.rebuild_audio([len(sig)], pred_t.astype(np.float32)[..., 0], stft.divide_phase(Xt)[..., 0], 8000, 32, 16)[0]
+    assert rebuild.sdr_db(ref_t, out_t) >= 60.0
+
+
+def test_model_objects_and_frozen_graph(workdir, tmp_path):
+    from fullycnnspeechenhancement_b200.freeze import FreezeEngine
+    w3 = network.random_weights("FullyCNNV3", seed=4, randomize_bn=True)
+    prefix = str(tmp_path / "v3.ckpt")
+    ckpt.write_checkpoint(prefix, w3)
+    pb = str(tmp_path / "v3.pb")
+    assert FreezeEngine("FullyCNNV3").freeze_graph(prefix, pb) == "decode_final/BiasAdd"
+    m = FullyCNNSEModelV3(is_training=False).restore(pb)             # frozen graph as weight source
+    assert m.param_count() == 32653
+    x = np.abs(np.random.default_rng(3).normal(0, 2, (1, 9, 129, 1))).astype(np.float32)
+    ref = network.forward("FullyCNNV3", w3, x, np.float64)
+    assert np.abs(m(x) - ref).max() / np.abs(ref).max() <= 1e-4
+    xt = torch.from_numpy(x).cuda()
+    yt = m(xt)                                                       # CUDA tensor in -> CUDA tensor out
+    assert yt.is_cuda and np.abs(yt.cpu().numpy() - ref).max() / np.abs(ref).max() <= 1e-4
+    with pytest.raises(RuntimeError):
+        FullyCNNSEModelV3(is_training=False)(x)                      # no weights loaded
+    with pytest.raises(KeyError):
+        FullyCNNSEModelV3(is_training=False).set_weights({"decode_final/kernel": x})

@@ -1,0 +1,128 @@
+"""CPU: the oracle against the committed golden vectors (which were produced by the unmodified
+reference code, tests/golden/make_golden.py) and against itself."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import network, rebuild, stft
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "stft_rebuild_ref.npz"))
+
+
+def test_frame_counts_and_indices_bit_exact(golden_dir):
+    fc = np.load(os.path.join(golden_dir, "frame_counts_ref.npz"))
+    for L, T, first, last in zip(fc["lengths"], fc["counts"], fc["first_start"], fc["last_start"]):
+        assert stft.frame_count(int(L)) == T
+        idx = stft.frame_indices(int(L))
+        assert idx.shape == (T, 256)
+        assert idx[0, 0] == first == 0
+        if last >= 0:                      # last frame starts inside the signal
+            assert idx[-1, 0] == last
+        assert idx[-1, 0] == (T - 1) * 128
+    # values called out in SURVEY.md section 8
+    for L, T in [(32000, 249), (16000, 124), (24001, 187), (64000, 499), (28800000, 224999), (256, 1), (100, 3)]:
+        assert stft.frame_count(L) == T
+
+
+def test_stft_matches_reference_bit_exact(g):
+    for seed, L in zip(g["case_seeds"], g["case_lengths"]):
+        x = g["wav_%d" % seed]
+        assert x.dtype == np.float32 and len(x) == L
+        X = stft.compute_spectrogram(x, 8000, 0.032, 0.016, 256, True)
+        assert np.array_equal(X, g["spec_%d" % seed])
+        assert np.array_equal(stft.power_spectrum(X), g["mag_%d" % seed])
+        assert np.array_equal(stft.divide_phase(X), g["phase_%d" % seed])
+
+
+def test_padding_batch_matches_reference(g):
+    seeds = g["case_seeds"][3:]
+    pb = stft.padding_batch([g["spec_%d" % s] for s in seeds])
+    assert np.array_equal(pb, g["padded_batch"])
+    # padded frames: magnitude 0, phase exactly 1+0j
+    T_short = g["spec_%d" % seeds[0]].shape[1]
+    assert np.all(stft.power_spectrum(pb)[0, T_short:] == 0)
+    assert np.all(stft.divide_phase(pb)[0, T_short:] == 1 + 0j)
+
+
+@pytest.mark.parametrize("nfft", [512, 256])
+def test_rebuild_matches_reference_bit_exact(g, nfft):
+    pb = g["padded_batch"]
+    phase = stft.divide_phase(pb).squeeze(-1)
+    lens = [int(x) for x in g["case_lengths"][3:]]
+    for loop in (False, True):
+        out = rebuild.rebuild_audio(lens, g["pred"], phase, 8000, 32.0, 16.0, nfft=nfft, faithful_loop=loop)
+        for i, L in enumerate(lens):
+            assert len(out[i]) == L
+            assert np.array_equal(out[i], g["rebuild%d_%d" % (nfft, i)])
+
+
+def test_de_emphasis_filter_equals_reference_loop():
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(3, 5000))
+    assert np.array_equal(rebuild.de_emphasis(x), rebuild.de_emphasis_loop(x))
+
+
+def test_pre_emphasis_is_float32_without_fma():
+    x = np.random.default_rng(1).normal(size=1000).astype(np.float32)
+    e = stft.pre_emphasis(x)
+    assert e.dtype == np.float32
+    manual = np.float32(x[1:]) - np.float32(np.float32(0.97) * x[:-1])
+    assert np.array_equal(e[1:], manual) and e[0] == x[0]
+
+
+def test_identity_network_known_answer():
+    """irfft 256 inverts the analysis (> 100 dB), the shipped
+    default irfft 512 does not (about -15 dB): both are reference behaviour."""
+    from fullycnnspeechenhancement_b200.synth import noisy_utterance
+    x = noisy_utterance(3, 32000)
+    X = stft.compute_spectrogram(x, 8000, 0.032, 0.016, 256, True).T[None]
+    mag, ph = stft.power_spectrum(X), stft.divide_phase(X)
+    y256 = rebuild.rebuild_audio([32000], mag, ph, nfft=256)[0]
+    y512 = rebuild.rebuild_audio([32000], mag, ph, nfft=512)[0]
+    assert rebuild.sdr_db(x.astype(np.float64), y256) > 100
+    assert -20 < rebuild.sdr_db(x.astype(np.float64), y512) < -10
+
+
+def test_parameter_counts_match_readme():
+    # readme.md:63-67 of the reference
+    assert network.trainable_param_count("FullyCNN") == 32765
+    assert network.trainable_param_count("FullyCNNV2") == 32192
+    assert network.trainable_param_count("FullyCNNV3") == 32653
+    # SURVEY.md section 8a MAC counts
+    assert network.mac_per_frame("FullyCNNV2", False) == 4054728
+    assert network.mac_per_frame("FullyCNNV2", True) == 3959092
+
+
+@pytest.mark.parametrize("arch", ["FullyCNN", "FullyCNNV2", "FullyCNNV3"])
+def test_network_two_evaluators_and_golden(arch, golden_dir):
+    n = np.load(os.path.join(golden_dir, "network_oracle.npz"))
+    w = network.random_weights(arch, seed=1234, randomize_bn=True)
+    s = [float(np.sum([np.sum(v.astype(np.float64)) for v in w.values()])),
+         float(np.sum([np.sum(np.abs(v.astype(np.float64))) for v in w.values()]))]
+    assert np.allclose(s, n["wsum_" + arch], rtol=0, atol=1e-9)      # seeded weights are reproducible
+    for T in (1, 7, 8, 9, 12):
+        x = n["x_%s_%d" % (arch, T)]
+        y = network.forward(arch, w, x, np.float64)
+        assert np.allclose(y, n["y_%s_%d" % (arch, T)], rtol=0, atol=1e-12)
+        y2 = network.forward_torch(arch, w, x, "float64")
+        assert np.abs(y - y2).max() <= 1e-12 * max(1.0, np.abs(y).max())
+        y32 = network.forward_torch(arch, w, x, "float32")
+        assert np.abs(y - y32).max() / np.abs(y).max() < 1e-5
+
+
+def test_network_padding_invariance():
+    arch = "FullyCNNV3"
+    w = network.random_weights(arch, seed=2)
+    rng = np.random.default_rng(0)
+    a = np.abs(rng.normal(size=(1, 6, 129, 1)))
+    batch = np.zeros((2, 11, 129, 1))
+    batch[0, :6] = a[0]
+    batch[1] = np.abs(rng.normal(size=(11, 129, 1)))
+    alone = network.forward(arch, w, a)
+    both = network.forward(arch, w, batch)
+    # frames whose 8-tap time window stays inside the 6 valid frames (+ zero padding == SAME padding)
+    assert np.allclose(alone[0, :2], both[0, :2], atol=1e-12)
