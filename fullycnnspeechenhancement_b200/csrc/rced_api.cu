@@ -160,21 +160,31 @@ static void pack_weights(int arch, const float* folded, float* packed) {
         const float* b = k + (size_t)s.kh * s.kw * s.cin * s.cout;
         float* w = packed + packed_w_off(arch, i);
         float* pb = packed + packed_b_off(arch, i);
-        if (i == nl - 1) {   // (1,129) layer, cout == 1: W[cin][132]
+        if (i == nl - 1) {   // (1,129) layer, cout == 1: W[cin][132] and the shifted copy S[t] = W[t+1]
+            float* sh = w + (size_t)s.cin * kFinalKP;
             for (int c = 0; c < s.cin; ++c)
-                for (int t = 0; t < s.kw; ++t) w[c * kFinalKP + t] = k[((size_t)t * s.cin + c) * s.cout];
+                for (int t = 0; t < s.kw; ++t) {
+                    const float v = k[((size_t)t * s.cin + c) * s.cout];
+                    w[c * kFinalKP + t] = v;
+                    if (t >= 1) sh[c * kFinalKP + t - 1] = v;
+                }
             pb[0] = b[0];
         } else {
-            const int ce = cin_eff(arch, i), cp = pad4(s.cout);
-            for (int c = 0; c < ce; ++c)
-                for (int t = 0; t < s.kw; ++t)
-                    for (int o = 0; o < s.cout; ++o) {
-                        // first layer: "channel" c is the time tap (kh index), cin == 1
-                        const size_t src = i == 0 ? (((size_t)c * s.kw + t) * s.cin + 0) * s.cout + o
-                                                  : (((size_t)0 * s.kw + t) * s.cin + c) * s.cout + o;
-                        w[((size_t)c * s.kw + t) * cp + o] = k[src];
-                    }
-            for (int o = 0; o < s.cout; ++o) pb[o] = b[o];
+            // part h owns channels [h*ch, h*ch+ch); per part: W[cin_eff][kw][ch] (each input
+            // channel's block padded to 16 bytes), channels beyond cout stay zero
+            const int ce = cin_eff(arch, i), ch = ch_part(arch, i), cib = ci_block(arch, i);
+            for (int h = 0; h < kSplit; ++h)
+                for (int c = 0; c < ce; ++c)
+                    for (int t = 0; t < s.kw; ++t)
+                        for (int o = 0; o < ch; ++o) {
+                            const int og = h * ch + o;
+                            if (og >= s.cout) continue;
+                            // first layer: "channel" c is the time tap (kh index), cin == 1
+                            const size_t src = i == 0 ? (((size_t)c * s.kw + t) * s.cin + 0) * s.cout + og
+                                                      : (((size_t)0 * s.kw + t) * s.cin + c) * s.cout + og;
+                            w[((size_t)h * ce + c) * cib + (size_t)t * ch + o] = k[src];
+                        }
+            for (int o = 0; o < s.cout; ++o) pb[(o / ch) * pad4(ch) + (o % ch)] = b[o];
         }
     }
 }
@@ -243,7 +253,9 @@ int rced_debug_layout(int arch, int64_t* out, int n) {
     out[2] = wide_floats(arch);
     out[3] = (int64_t)net_smem_bytes_rt(arch);
     out[4] = skip_total_cols(arch);
-    out[5] = out[6] = out[7] = 0;
+    out[5] = kSplit;
+    out[6] = combine_off(arch);
+    out[7] = 0;
     for (int i = 0; i < num_layers(arch); ++i) {
         const LSpec s = spec(arch, i);
         out[8 + 4 * i] = packed_w_off(arch, i);
@@ -315,7 +327,7 @@ int rced_set_skip_in_tmem(rced_handle* h, int enable) {
     if (!h) return fail(RCED_ERR_ARG, "null handle");
     if (!enable && !h->d_scratch) {
         DeviceGuard guard(h->device);
-        const size_t bytes = (size_t)h->num_sms * kWarpsPerCta * 512 * 32 * sizeof(float);
+        const size_t bytes = (size_t)h->num_sms * kFramesPerCta * 512 * 32 * sizeof(float);
         cudaError_t e = cudaMalloc(&h->d_scratch, bytes);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(skip scratch)");
     }

@@ -22,7 +22,10 @@ constexpr int kRowBin0 = 8;       // offset of bin 0 inside a row
 constexpr int kWS = 196;          // row stride of the "wide" layout read by the (1,129) layer
 constexpr int kWideBin0 = 64;     // 64-float zero halo on each side (SAME pad of k=129)
 constexpr int kFinalKP = 132;     // 129 taps padded to a multiple of 4
-constexpr int kWarpsPerCta = 4;   // one frame pipeline per warp, one warp per SM sub-partition
+constexpr int kFramesPerCta = 4;  // one frame pipeline per SM sub-partition ...
+constexpr int kSplit = 2;         // ... run by kSplit warps that share the frame's output channels
+constexpr int kWarpsPerCta = kFramesPerCta * kSplit;   // warp w: frame slot w % 4, channel part w / 4
+constexpr int kCombine = 136;     // per-slot scratch the two parts of the (1,129) layer meet in
 constexpr int kMaxLayers = 16;
 
 struct LSpec {
@@ -80,6 +83,7 @@ RCED_HD constexpr LSpec spec(int arch, int i) {
 }
 
 RCED_HD constexpr int pad4(int x) { return (x + 3) & ~3; }
+RCED_HD constexpr int pad2(int x) { return (x + 1) & ~1; }
 
 // "input channels" the kernel iterates over: the 8 time taps for the first layer (cin == 1),
 // the real channel count elsewhere.
@@ -96,15 +100,22 @@ RCED_HD constexpr int64_t folded_off(int arch, int i) {
 }
 RCED_HD constexpr int64_t folded_count(int arch) { return folded_off(arch, num_layers(arch)); }
 
+// ---- channel split of a conv layer over the kSplit warps of a frame ---------------------
+// part h owns output channels [h*ch_part, (h+1)*ch_part) (those >= cout are zero padding); the
+// count is even because the inner loop works on channel PAIRS (packed fma.rn.f32x2).
+RCED_HD constexpr int ch_part(int arch, int i) { return pad2((spec(arch, i).cout + kSplit - 1) / kSplit); }
+// floats of one part's weights for one input channel: [kw][ch_part], padded to 16 bytes
+RCED_HD constexpr int ci_block(int arch, int i) { return pad4(spec(arch, i).kw * ch_part(arch, i)); }
+
 // ---- packed shared-memory weight image -----------------------------------------------
-// conv layer i : W[cin_eff][kw][pad4(cout)] then bias[pad4(cout)]
-// final layer  : W[cin][kFinalKP] then bias[4]
+// conv layer i : W[part][cin_eff][ci_block] then bias[part][pad4(ch_part)]
+// final layer  : W[cin][kFinalKP], S[cin][kFinalKP] (S[t] = W[t+1], the odd-bin pairing) then bias[4]
 RCED_HD constexpr int packed_w_floats(int arch, int i) {
-    return i == num_layers(arch) - 1 ? spec(arch, i).cin * kFinalKP
-                                     : cin_eff(arch, i) * spec(arch, i).kw * pad4(spec(arch, i).cout);
+    return i == num_layers(arch) - 1 ? 2 * spec(arch, i).cin * kFinalKP
+                                     : kSplit * cin_eff(arch, i) * ci_block(arch, i);
 }
 RCED_HD constexpr int packed_b_floats(int arch, int i) {
-    return i == num_layers(arch) - 1 ? 4 : pad4(spec(arch, i).cout);
+    return i == num_layers(arch) - 1 ? 4 : kSplit * pad4(ch_part(arch, i));
 }
 RCED_HD constexpr int packed_w_off(int arch, int i) {
     int o = 0;
@@ -131,13 +142,24 @@ RCED_HD constexpr int stage_row(int arch) { return (wide_floats(arch) + kRS - 1)
 RCED_HD constexpr int slot_rows(int arch) {
     return max_channels(arch) > stage_row(arch) + 9 ? max_channels(arch) : stage_row(arch) + 9;
 }
-RCED_HD constexpr int slot_floats(int arch) { return slot_rows(arch) * kRS + 8; }
+RCED_HD constexpr int slot_floats(int arch) { return slot_rows(arch) * kRS + 8 + kCombine; }
+RCED_HD constexpr int combine_off(int arch) { return slot_rows(arch) * kRS + 8; }
 
-// ---- tensor-memory columns of the skip slots (per thread: 4 bins x cout + 1 tail value) ----
-RCED_HD constexpr int skip_cols(int arch, int slot) {
+// ---- tensor-memory columns of the skip slots ------------------------------------------------
+// per part: 4 bins x ch_part channels + 1 value of bin 128 (lane == channel), parts back to back
+RCED_HD constexpr int skip_part_cols(int arch, int slot) {
     for (int i = 0; i < num_layers(arch); ++i)
-        if (spec(arch, i).save == slot) return 4 * spec(arch, i).cout + 1;
+        if (spec(arch, i).save == slot) return 4 * ch_part(arch, i) + 1;
     return 0;
+}
+RCED_HD constexpr int skip_cols(int arch, int slot) { return kSplit * skip_part_cols(arch, slot); }
+// a layer that adds skip slot s must split its channels exactly like the layer that saved it
+RCED_HD constexpr bool skip_split_consistent(int arch) {
+    for (int i = 0; i < num_layers(arch); ++i) {
+        if (spec(arch, i).add < 0) continue;
+        if (4 * ch_part(arch, i) + 1 != skip_part_cols(arch, spec(arch, i).add)) return false;
+    }
+    return true;
 }
 RCED_HD constexpr int skip_col_base(int arch, int slot) {
     int o = 0;
@@ -165,6 +187,7 @@ RCED_HD constexpr int64_t mac_per_frame(int arch, bool valid_only) {
     return total;
 }
 
+static_assert(skip_split_consistent(1) && skip_split_consistent(2) && skip_split_consistent(3), "skip split mismatch");
 static_assert(skip_total_cols(1) <= 512 && skip_total_cols(2) <= 512 && skip_total_cols(3) <= 512,
               "skip tensors must fit the 512 tensor-memory columns of one lane quadrant");
 

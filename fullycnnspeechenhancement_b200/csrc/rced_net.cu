@@ -4,16 +4,22 @@
 // (model_utils/tester.py:85-90) for the graphs of model_utils/model.py.
 //
 // Design:
-//  * persistent grid, one CTA of 4 warps per SM, one warp per SM sub-partition;
-//  * every warp is an independent FRAME PIPELINE: it takes one spectrogram frame through
-//    all 10/16 layers; lane l owns frequency bins 4l..4l+3 for ALL output channels of the
-//    current layer (register tile 4 x cout, FP32 FFMA), bin 128 is a small extra phase with
-//    lane == output channel;
-//  * all BN-folded weights (about 130 KB) sit in shared memory for the whole kernel, brought
-//    in once per CTA with bulk async copies (cp.async.bulk + mbarrier);
-//  * layer activations live in a per-warp shared-memory slot and are overwritten in place
-//    (the whole layer output is held in registers before the first store), so no block-level
-//    barrier exists anywhere in the layer loop -- only __syncwarp;
+//  * persistent grid, one CTA of 8 warps per SM.  Each SM sub-partition runs one FRAME PIPELINE
+//    made of the two warps w and w+4: they take one spectrogram frame through all 10/16 layers
+//    and split every layer's output channels in halves (part = w / 4).  Two warps per scheduler
+//    hide each other's shared-memory and pipeline latencies;
+//  * lane l owns frequency bins 4l..4l+3 for its part's channels; the register tile is
+//    4 bins x (channels / 2) PAIRS and the inner loop is the packed FP32 FMA of Blackwell
+//    (fma.rn.f32x2 -> FFMA2: the activation is broadcast, the weight pair comes straight out of
+//    an LDS.128, the accumulator pair is a 64-bit register) -- half the issue slots and
+//    register-file reads of scalar FFMA per flop, so loads issue in the FMA pipe's shadow;
+//    bin 128 is a small extra phase with lane == output channel;
+//  * all BN-folded weights (about 145 KB, laid out per part) sit in shared memory for the whole
+//    kernel, brought in once per CTA with bulk async copies (cp.async.bulk + mbarrier);
+//  * layer activations live in a per-frame shared-memory slot and are overwritten in place (the
+//    whole layer output is held in registers before the first store); the two warps of a frame
+//    meet at a 64-thread named barrier before and after the stores -- there is no CTA-wide
+//    barrier anywhere in the layer loop;
 //  * encoder outputs needed later by decoder skip connections are parked in TENSOR MEMORY
 //    (tcgen05.st), thread-private, and loaded back (tcgen05.ld) straight into the accumulator
 //    registers of the consuming decoder layer.  Global memory only sees the input magnitude
@@ -130,16 +136,45 @@ struct SkipStore<false> {
 };
 
 // ------------------------------------------------------------------------------------------
-// one conv_bn_relu layer (all but the last) for one frame, executed by one warp
+// packed FP32 pairs (fma.rn.f32x2 -> FFMA2) and the 64-thread frame barrier
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// d += {x, x} * w      (ptxas encodes the duplicated activation as a broadcast .F32 operand)
+__device__ __forceinline__ void fma2_bcast(u64& d, float x, u64 w) {
+    const u64 xx = pack2(x, x);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(xx), "l"(w));
+}
+// d += a * b, both packed
+__device__ __forceinline__ void fma2(u64& d, u64 a, u64 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+// the kSplit warps of one frame pipeline (named barrier 1 + frame slot, 32 * kSplit threads)
+__device__ __forceinline__ void frame_bar(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * kSplit) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// one conv_bn_relu layer (all but the last) for one frame; executed by the kSplit warps of the
+// frame, `part` selects this warp's output channels [part * CH, part * CH + CH)
 // ------------------------------------------------------------------------------------------
 template <int ARCH, bool TM, int LI>
 __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* __restrict__ slot, const int lane,
-                                           const SkipStore<TM>& sk) {
+                                           const int part, const int bar_id, const SkipStore<TM>& sk) {
     constexpr LSpec S = spec(ARCH, LI);
     constexpr int NL = num_layers(ARCH);
     constexpr int CIN = cin_eff(ARCH, LI);
     constexpr int COUT = S.cout;
-    constexpr int COUTP = pad4(COUT);
+    constexpr int CH = ch_part(ARCH, LI);              // channels of this warp (even)
+    constexpr int NP = CH / 2;                         // channel pairs
+    constexpr int CIB = ci_block(ARCH, LI);            // weight floats per input channel per part
     constexpr int KW = S.kw;
     constexpr int PADL = (KW - 1) / 2;
     constexpr bool WIDEWIN = PADL > 4;                 // window of 20 floats instead of 12
@@ -147,44 +182,49 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
     constexpr int XB = (WIDEWIN ? 8 : 4) - PADL;       // x[XB + f + k] is bin 4l+f+k-PADL
     constexpr bool OUT_WIDE = (LI == NL - 2);          // feeds the (1,129) layer
     constexpr bool PRE_ADD = (S.add >= 0) && !S.after; // skip pre-loaded into the accumulators
-    static_assert(PADL <= 8, "window loader covers SAME pads up to 8");
-    static_assert(COUT <= 32, "tail phase maps output channels to lanes");
+    constexpr bool POST_ADD = (S.add >= 0) && S.after; // V3: added after the ReLU
+    static_assert(PADL <= 7, "window loader covers SAME pads up to 7");
+    static_assert(CH <= 32, "tail phase maps output channels to lanes");
 
-    const float* __restrict__ W = sW + packed_w_off(ARCH, LI);
-    const float* __restrict__ B = sW + packed_b_off(ARCH, LI);
+    const float* __restrict__ W = sW + packed_w_off(ARCH, LI) + part * (CIN * CIB);
+    const float* __restrict__ B = sW + packed_b_off(ARCH, LI) + part * pad4(CH);
     const float* __restrict__ in0 = slot + (LI == 0 ? stage_row(ARCH) * kRS : 0);
     const float* __restrict__ inx = in0 + (WIDEWIN ? 0 : 4) + 4 * lane;
-    const int cl = lane < COUTP ? lane : COUTP - 1;    // tail phase: this lane's output channel
+    const int cbase = part * CH;                       // first output channel of this warp
+    const int cl = lane < CH ? lane : CH - 1;          // tail phase: this lane's channel (local)
+    const int col_add = S.add >= 0 ? skip_col_base(ARCH, S.add >= 0 ? S.add : 0) + part * (4 * CH + 1) : 0;
+    const int col_save = S.save >= 0 ? skip_col_base(ARCH, S.save >= 0 ? S.save : 0) + part * (4 * CH + 1) : 0;
 
-    float acc[4][COUT];
+    u64 acc[4][NP];      // acc[f][j] = channels (2j, 2j+1) of bin 4l+f
     float tacc;
 
     if constexpr (PRE_ADD) {
-        constexpr int col = skip_col_base(ARCH, S.add);
+        float s[4][CH];
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) sk.ld4(col + 4 * c, acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-        sk.ld1(col + 4 * COUT, tacc);
+        for (int c = 0; c < CH; ++c) sk.ld4(col_add + 4 * c, s[0][c], s[1][c], s[2][c], s[3][c]);
+        sk.ld1(col_add + 4 * CH, tacc);
         sk.wait_ld();
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-            reg_fence4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-            const float b = B[c];
-#pragma unroll
-            for (int f = 0; f < 4; ++f) acc[f][c] += b;
-        }
+        for (int c = 0; c < CH; ++c) reg_fence4(s[0][c], s[1][c], s[2][c], s[3][c]);
         reg_fence1(tacc);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const float b0 = B[2 * j], b1 = B[2 * j + 1];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[f][j] = pack2(s[f][2 * j] + b0, s[f][2 * j + 1] + b1);
+        }
         tacc += B[cl];
     } else {
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-            const float b = B[c];
+        for (int j = 0; j < NP; ++j) {
+            const u64 b = pack2(B[2 * j], B[2 * j + 1]);
 #pragma unroll
-            for (int f = 0; f < 4; ++f) acc[f][c] = b;
+            for (int f = 0; f < 4; ++f) acc[f][j] = b;
         }
         tacc = B[cl];
     }
 
-    // ---- main phase: bins 4l..4l+3, all output channels ----------------------------------
+    // ---- main phase: bins 4l..4l+3, this warp's channel pairs -------------------------------
 #pragma unroll 1
     for (int ci = 0; ci < CIN; ++ci) {
         float x[NX4 * 4];
@@ -194,19 +234,18 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
             const float4 v = xp[i];
             x[4 * i + 0] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
-        const float4* wp = reinterpret_cast<const float4*>(W + ci * (KW * COUTP));
+        // [kw][CH] weights of this input channel as one flat run of pairs; warp-uniform
+        // addresses (broadcast LDS.128 = two pairs), a pair never straddles a 16-byte word
+        const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(W + ci * CIB);
 #pragma unroll
         for (int k = 0; k < KW; ++k) {
-            float w[COUTP];
 #pragma unroll
-            for (int j = 0; j < COUTP / 4; ++j) {
-                const float4 v = wp[k * (COUTP / 4) + j];   // warp-uniform address: broadcast
-                w[4 * j + 0] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
-            }
+            for (int j = 0; j < NP; ++j) {
+                const int P = k * NP + j;
+                const ulonglong2 q = wq[P >> 1];
+                const u64 w = (P & 1) ? q.y : q.x;
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) {
-#pragma unroll
-                for (int f = 0; f < 4; ++f) acc[f][c] = fmaf(x[XB + f + k], w[c], acc[f][c]);
+                for (int f = 0; f < 4; ++f) fma2_bcast(acc[f][j], x[XB + f + k], w);
             }
         }
     }
@@ -219,96 +258,124 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
         for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
             for (int k = 0; k <= PADL; ++k)
-                tacc = fmaf(xt[ci * kRS + k], wt[(ci * KW + k) * COUTP], tacc);
+                tacc = fmaf(xt[ci * kRS + k], wt[ci * CIB + k * CH], tacc);
         }
     }
 
     // ---- epilogue ----------------------------------------------------------------------------
     float tsk = 0.f;
-    if constexpr (S.add >= 0 && S.after) {   // V3: relu first, then add the skip (no second relu)
-        constexpr int col = skip_col_base(ARCH, S.add);
-        sk.ld1(col + 4 * COUT, tsk);
-    }
-    __syncwarp();   // every lane has finished reading this layer's input (it is overwritten below)
+    if constexpr (POST_ADD) sk.ld1(col_add + 4 * CH, tsk);   // V3: relu first, then add the skip (no second relu)
+    frame_bar(bar_id);   // every lane of the frame has finished reading this layer's input (overwritten below)
 
     if constexpr (OUT_WIDE) {
         // the (1,129) layer reads rows of stride kWS with 64 zeros either side: clear, then fill
         float4* z = reinterpret_cast<float4*>(slot);
-        for (int i = lane; i < wide_floats(ARCH) / 4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
+        for (int i = part * 32 + lane; i < wide_floats(ARCH) / 4; i += 32 * kSplit) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        frame_bar(bar_id);
     }
 
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) {
-        float v0 = acc[0][c], v1 = acc[1][c], v2 = acc[2][c], v3 = acc[3][c];
-        if constexpr (S.relu) {
-            v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+    for (int c = 0; c < CH; ++c) {
+        float v[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            float lo, hi;
+            unpack2(acc[f][c >> 1], lo, hi);
+            v[f] = (c & 1) ? hi : lo;
+            if constexpr (S.relu) v[f] = fmaxf(v[f], 0.f);
         }
-        if constexpr (S.add >= 0 && S.after) {
-            constexpr int col = skip_col_base(ARCH, S.add);
+        if constexpr (POST_ADD) {
             float s0, s1, s2, s3;
-            sk.ld4(col + 4 * c, s0, s1, s2, s3);
+            sk.ld4(col_add + 4 * c, s0, s1, s2, s3);
             sk.wait_ld();
             reg_fence4(s0, s1, s2, s3);
-            v0 += s0; v1 += s1; v2 += s2; v3 += s3;
+            v[0] += s0; v[1] += s1; v[2] += s2; v[3] += s3;
         }
-        if constexpr (S.save >= 0) sk.st4(skip_col_base(ARCH, S.save) + 4 * c, v0, v1, v2, v3);
-        float* o = OUT_WIDE ? slot + c * kWS + kWideBin0 + 4 * lane : slot + c * kRS + kRowBin0 + 4 * lane;
-        *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
+        if constexpr (S.save >= 0) sk.st4(col_save + 4 * c, v[0], v[1], v[2], v[3]);
+        if (cbase + c < COUT) {   // channels beyond cout are the zero padding of the last part
+            float* o = OUT_WIDE ? slot + (cbase + c) * kWS + kWideBin0 + 4 * lane : slot + (cbase + c) * kRS + kRowBin0 + 4 * lane;
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        }
     }
     {
         float t = tacc;
         if constexpr (S.relu) t = fmaxf(t, 0.f);
-        if constexpr (S.add >= 0 && S.after) {
+        if constexpr (POST_ADD) {
             sk.wait_ld();
             reg_fence1(tsk);
             t += tsk;
         }
-        if constexpr (S.save >= 0) sk.st1(skip_col_base(ARCH, S.save) + 4 * COUT, t);
-        if (lane < COUT) {
-            float* o = OUT_WIDE ? slot + lane * kWS + kWideBin0 + 128 : slot + lane * kRS + kRowBin0 + 128;
+        if constexpr (S.save >= 0) sk.st1(col_save + 4 * CH, t);
+        if (lane < CH && cbase + lane < COUT) {
+            float* o = OUT_WIDE ? slot + (cbase + lane) * kWS + kWideBin0 + 128 : slot + (cbase + lane) * kRS + kRowBin0 + 128;
             *o = t;
         }
     }
     if constexpr (S.save >= 0) sk.wait_st();
-    __syncwarp();
+    frame_bar(bar_id);   // the layer output is complete and visible to both warps
 }
 
 // ------------------------------------------------------------------------------------------
-// the (1,129) output layer: cout = 1, no BN / ReLU; reads the wide layout, writes global memory
+// the (1,129) output layer: cout = 1, no BN / ReLU; reads the wide layout, writes global memory.
+// The parts split the INPUT channels; part 1 hands its partial sums to part 0 through `comb`.
+// Packed pairs run along the taps: bin b pairs taps (k, k+1) with b + k even, so that both the
+// activation pair and the weight pair are aligned 64-bit words -- even bins read W, odd bins
+// read S (S[t] = W[t+1]) and take their tap 0 as a scalar FMA, even bins their tap 128.
 // ------------------------------------------------------------------------------------------
 template <int ARCH>
-__device__ __forceinline__ void final_layer(const float* __restrict__ sW, const float* __restrict__ slot, const int lane,
-                                            float* __restrict__ out_row) {
+__device__ __forceinline__ void final_layer(const float* __restrict__ sW, float* __restrict__ slot, const int lane,
+                                            const int part, const int bar_id, float* __restrict__ out_row) {
     constexpr int LI = num_layers(ARCH) - 1;
     constexpr int CIN = spec(ARCH, LI).cin;
+    constexpr int CPART = (CIN + kSplit - 1) / kSplit;
     const float* __restrict__ Wf = sW + packed_w_off(ARCH, LI);
+    const float* __restrict__ Sf = Wf + CIN * kFinalKP;
     const float bias = sW[packed_b_off(ARCH, LI)];
+    float* comb = slot + combine_off(ARCH);
+    const int c0 = part * CPART;
+    const int c1 = c0 + CPART < CIN ? c0 + CPART : CIN;
 
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    u64 a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;   // (even-tap, odd-tap) partial sums of bins 4l..4l+3
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;     // the unpaired taps
 #pragma unroll 1
-    for (int ci = 0; ci < CIN; ++ci) {
+    for (int ci = c0; ci < c1; ++ci) {
         // out bin 4l+j, tap k reads wide offset 4l + j + k
-        const float4* row = reinterpret_cast<const float4*>(slot + ci * kWS + 4 * lane);
-        const float4* w4 = reinterpret_cast<const float4*>(Wf + ci * kFinalKP);
-        float4 xa = row[0];
+        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(slot + ci * kWS + 4 * lane);
+        const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(Wf + ci * kFinalKP);
+        const ulonglong2* s4 = reinterpret_cast<const ulonglong2*>(Sf + ci * kFinalKP);
+        ulonglong2 xa = row[0];
+        {
+            float x0, x1, x2, x3;
+            unpack2(xa.x, x0, x1);
+            unpack2(xa.y, x2, x3);
+            const float w0 = Wf[ci * kFinalKP];
+            l1 = fmaf(x1, w0, l1);
+            l3 = fmaf(x3, w0, l3);
+        }
 #pragma unroll 8
         for (int q = 0; q < 32; ++q) {
-            const float4 xb = row[q + 1];
-            const float4 w = w4[q];
-            a0 = fmaf(xa.x, w.x, a0); a0 = fmaf(xa.y, w.y, a0); a0 = fmaf(xa.z, w.z, a0); a0 = fmaf(xa.w, w.w, a0);
-            a1 = fmaf(xa.y, w.x, a1); a1 = fmaf(xa.z, w.y, a1); a1 = fmaf(xa.w, w.z, a1); a1 = fmaf(xb.x, w.w, a1);
-            a2 = fmaf(xa.z, w.x, a2); a2 = fmaf(xa.w, w.y, a2); a2 = fmaf(xb.x, w.z, a2); a2 = fmaf(xb.y, w.w, a2);
-            a3 = fmaf(xa.w, w.x, a3); a3 = fmaf(xb.x, w.y, a3); a3 = fmaf(xb.y, w.z, a3); a3 = fmaf(xb.z, w.w, a3);
+            const ulonglong2 xb = row[q + 1];
+            const ulonglong2 w = w4[q];
+            const ulonglong2 s = s4[q];
+            fma2(a0, xa.x, w.x); fma2(a0, xa.y, w.y);
+            fma2(a2, xa.y, w.x); fma2(a2, xb.x, w.y);
+            fma2(a1, xa.y, s.x); fma2(a1, xb.x, s.y);
+            fma2(a3, xb.x, s.x); fma2(a3, xb.y, s.y);
             xa = xb;
         }
-        const float w128 = Wf[ci * kFinalKP + 128];
-        a0 = fmaf(xa.x, w128, a0); a1 = fmaf(xa.y, w128, a1); a2 = fmaf(xa.z, w128, a2); a3 = fmaf(xa.w, w128, a3);
+        {
+            float x0, x1, x2, x3;
+            unpack2(xa.x, x0, x1);
+            unpack2(xa.y, x2, x3);
+            const float w128 = Wf[ci * kFinalKP + 128];
+            l0 = fmaf(x0, w128, l0);
+            l2 = fmaf(x2, w128, l2);
+        }
     }
     // bin 128: taps 0..64 over wide offsets 128..192, split across lanes, shuffle-reduced
     float t = 0.f;
 #pragma unroll 2
-    for (int ci = 0; ci < CIN; ++ci) {
+    for (int ci = c0; ci < c1; ++ci) {
         const float* r = slot + ci * kWS + 128;
         const float* w = Wf + ci * kFinalKP;
         t = fmaf(r[lane], w[lane], t);
@@ -318,16 +385,31 @@ __device__ __forceinline__ void final_layer(const float* __restrict__ sW, const 
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
 
-    float* o = out_row + 4 * lane;
-    o[0] = a0 + bias; o[1] = a1 + bias; o[2] = a2 + bias; o[3] = a3 + bias;
-    if (lane == 0) out_row[128] = t + bias;
+    float e, o, r0, r1, r2, r3;
+    unpack2(a0, e, o); r0 = (e + o) + l0;
+    unpack2(a1, e, o); r1 = (e + o) + l1;
+    unpack2(a2, e, o); r2 = (e + o) + l2;
+    unpack2(a3, e, o); r3 = (e + o) + l3;
+
+    if (part != 0) {
+        *reinterpret_cast<float4*>(comb + 4 * lane) = make_float4(r0, r1, r2, r3);
+        if (lane == 0) comb[128] = t;
+    }
+    frame_bar(bar_id);   // partial sums are in `comb`; nobody reads the wide layout any more
+    if (part == 0) {
+        const float4 c = *reinterpret_cast<const float4*>(comb + 4 * lane);
+        float* op = out_row + 4 * lane;
+        op[0] = (r0 + c.x) + bias; op[1] = (r1 + c.y) + bias; op[2] = (r2 + c.z) + bias; op[3] = (r3 + c.w) + bias;
+        if (lane == 0) out_row[128] = (t + comb[128]) + bias;
+    }
 }
 
 template <int ARCH, bool TM, int LI>
-__device__ __forceinline__ void run_conv_layers(const float* sW, float* slot, int lane, const SkipStore<TM>& sk) {
+__device__ __forceinline__ void run_conv_layers(const float* sW, float* slot, int lane, int part, int bar_id,
+                                                const SkipStore<TM>& sk) {
     if constexpr (LI < num_layers(ARCH) - 1) {
-        conv_layer<ARCH, TM, LI>(sW, slot, lane, sk);
-        run_conv_layers<ARCH, TM, LI + 1>(sW, slot, lane, sk);
+        conv_layer<ARCH, TM, LI>(sW, slot, lane, part, bar_id, sk);
+        run_conv_layers<ARCH, TM, LI + 1>(sW, slot, lane, part, bar_id, sk);
     }
 }
 
@@ -351,22 +433,25 @@ __device__ __forceinline__ FrameLoc locate(const long long* __restrict__ row_off
 }
 
 // Stage the 8 input rows (frames g-3 .. g+4, zeros outside the utterance) of frame g into rows
-// stage_row .. stage_row+7 of the slot with asynchronous 4-byte copies.
+// stage_row .. stage_row+7 of the slot with asynchronous 4-byte copies; each part of the frame
+// brings in 8 / kSplit of the rows.
 template <int ARCH>
-__device__ __forceinline__ void prefetch_frame(const NetParams& p, long long g, float* slot, int lane) {
+__device__ __forceinline__ void prefetch_frame(const NetParams& p, long long g, float* slot, int lane, int part) {
     constexpr int SR = stage_row(ARCH);
+    constexpr int RPP = 8 / kSplit;
     const FrameLoc loc = locate(p.row_off, p.n_utt, g);
     // halo offsets 1..7 of the 9 rows touched (offset 0 is bin 128 of the row before)
-    for (int i = lane; i < 9 * 7; i += 32) slot[(SR + i / 7) * kRS + 1 + (i % 7)] = 0.f;
+    for (int i = part * 32 + lane; i < 9 * 7; i += 32 * kSplit) slot[(SR + i / 7) * kRS + 1 + (i % 7)] = 0.f;
 #pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
+    for (int d = 0; d < RPP; ++d) {
+        const int dt = part * RPP + d;
         const long long r = g + dt - 3;
         float* dst = slot + (SR + dt) * kRS + kRowBin0;
         if (r >= loc.lo && r < loc.hi) {
             const float* src = p.in + r * (long long)kBins;
-            const uint32_t d = smem_u32(dst + 4 * lane);
+            const uint32_t da = smem_u32(dst + 4 * lane);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cp_async4(d + 4 * j, src + 4 * lane + j);
+            for (int j = 0; j < 4; ++j) cp_async4(da + 4 * j, src + 4 * lane + j);
             if (lane == 0) cp_async4(smem_u32(dst + 128), src + 128);
         } else {
             *reinterpret_cast<float4*>(dst + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -392,7 +477,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float* slot = slots + warp * SLOT;
+    const int fs = warp & (kFramesPerCta - 1);   // frame slot == SM sub-partition == tensor-memory lane quadrant
+    const int part = warp / kFramesPerCta;       // which share of every layer's output channels
+    const int bar_id = 1 + fs;
+    float* slot = slots + fs * SLOT;
 
     // ---- weights -> shared memory with bulk async copies -----------------------------------
     const uint32_t bar = smem_u32(&s_bar);
@@ -410,8 +498,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
             bulk_g2s(smem_u32(sW) + o, reinterpret_cast<const char*>(p.packed) + o, n, bar);
         }
     }
-    // meanwhile: clear this warp's slot (all halos must read as zero)
-    for (int i = lane; i < SLOT / 4; i += 32) reinterpret_cast<float4*>(slot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // meanwhile: clear this frame's slot (all halos must read as zero)
+    for (int i = part * 32 + lane; i < SLOT / 4; i += 32 * kSplit)
+        reinterpret_cast<float4*>(slot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     SkipStore<TM> sk;
     if constexpr (TM) {
@@ -419,30 +508,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
         tmem_fence_before();
         __syncthreads();
         tmem_fence_after();
-        sk.base = s_tmem + ((uint32_t)(warp & 3) << 21);   // lane field (bits 31:16) = 32 * (warp % 4)
+        sk.base = s_tmem + ((uint32_t)fs << 21);   // lane field (bits 31:16) = 32 * (warp % 4)
     } else {
-        sk.base = p.skip_scratch + ((size_t)blockIdx.x * kWarpsPerCta + warp) * (512 * 32) + lane;
+        sk.base = p.skip_scratch + ((size_t)blockIdx.x * kFramesPerCta + fs) * (512 * 32) + lane;
         __syncthreads();
     }
     mbar_wait(bar, 0);
 
-    const long long stride = (long long)gridDim.x * kWarpsPerCta;
-    long long g = (long long)blockIdx.x * kWarpsPerCta + warp;
-    __syncwarp();
-    if (g < p.total_rows) prefetch_frame<ARCH>(p, g, slot, lane);
+    const long long stride = (long long)gridDim.x * kFramesPerCta;
+    long long g = (long long)blockIdx.x * kFramesPerCta + fs;
+    if (g < p.total_rows) prefetch_frame<ARCH>(p, g, slot, lane, part);
 
     for (; g < p.total_rows; g += stride) {
         cp_async_wait_all();
-        __syncwarp();
-        run_conv_layers<ARCH, TM, 0>(sW, slot, lane, sk);
+        frame_bar(bar_id);   // input rows and restored halos are visible to both warps
+        run_conv_layers<ARCH, TM, 0>(sW, slot, lane, part, bar_id, sk);
         // the wide layout sits below row SR: the next frame's input can land while the last layer runs
         const long long gn = g + stride;
-        if (gn < p.total_rows) prefetch_frame<ARCH>(p, gn, slot, lane);
-        final_layer<ARCH>(sW, slot, lane, p.out + g * (long long)kBins);
-        __syncwarp();
+        if (gn < p.total_rows) prefetch_frame<ARCH>(p, gn, slot, lane, part);
+        final_layer<ARCH>(sW, slot, lane, part, bar_id, p.out + g * (long long)kBins);
         // the wide layout overwrote the halos of rows 0..SR: restore their zeros
-        for (int i = lane; i < (SR + 1) * 7; i += 32) slot[(i / 7) * kRS + 1 + (i % 7)] = 0.f;
-        __syncwarp();
+        for (int i = part * 32 + lane; i < (SR + 1) * 7; i += 32 * kSplit) slot[(i / 7) * kRS + 1 + (i % 7)] = 0.f;
     }
 
     if constexpr (TM) {
@@ -457,18 +543,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
 // ------------------------------------------------------------------------------------------
 template <int ARCH>
 constexpr size_t net_smem_bytes() {
-    return (size_t)(pad4(packed_count(ARCH)) + kWarpsPerCta * slot_floats(ARCH)) * sizeof(float);
+    return (size_t)(pad4(packed_count(ARCH)) + kFramesPerCta * slot_floats(ARCH)) * sizeof(float);
 }
 
 template <int ARCH, bool TM>
 static cudaError_t launch_net_t(const NetParams& p, int num_sms, cudaStream_t stream) {
     constexpr size_t smem = net_smem_bytes<ARCH>();
     static_assert(smem <= 227 * 1024, "weights + activation slots must fit one SM's shared memory");
-    static bool configured = false;   // per template instance; the attribute is per-device-per-function
-    (void)configured;
+    static_assert(slot_floats(ARCH) % 4 == 0 && pad4(packed_count(ARCH)) % 4 == 0, "16-byte aligned slots");
     cudaError_t e = cudaFuncSetAttribute(rced_net_kernel<ARCH, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    long long ctas = (p.total_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+    long long ctas = (p.total_rows + kFramesPerCta - 1) / kFramesPerCta;
     if (ctas > num_sms) ctas = num_sms;
     if (ctas < 1) return cudaSuccess;
     rced_net_kernel<ARCH, TM><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
