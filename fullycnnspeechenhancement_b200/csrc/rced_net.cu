@@ -183,6 +183,10 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
     constexpr bool OUT_WIDE = (LI == NL - 2);          // feeds the (1,129) layer
     constexpr bool PRE_ADD = (S.add >= 0) && !S.after; // skip pre-loaded into the accumulators
     constexpr bool POST_ADD = (S.add >= 0) && S.after; // V3: added after the ReLU
+    // Both parts run the SAME instruction stream with run-time offsets: they share one
+    // scheduler's instruction cache.  (Measured alternatives, tools/k2_bench: per-part
+    // instantiations with an uneven 7+6 pair split, or predicating off the padded pair of the
+    // last part, both cost 6-8% -- instruction-cache misses / predicated FFMA2 still take the pipe.)
     static_assert(PADL <= 7, "window loader covers SAME pads up to 7");
     static_assert(CH <= 32, "tail phase maps output channels to lanes");
 
@@ -225,15 +229,64 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
     }
 
     // ---- main phase: bins 4l..4l+3, this warp's channel pairs -------------------------------
-#pragma unroll 1
+    constexpr int NQ = CIB / 4;                        // 16-byte weight words per input channel
+    const float* wt = W + cl;                          // bin-128 phase: this lane's channel
+#ifndef RCED_PREFETCH
+#define RCED_PREFETCH 1
+#endif
+#ifndef RCED_UNROLL_SMALL
+#define RCED_UNROLL_SMALL 2
+#endif
+#ifndef RCED_TAIL_LDS
+#define RCED_TAIL_LDS 0
+#endif
+    constexpr int BODY = KW * NP * 4;                  // packed FMAs per input channel
+    constexpr int UNR = BODY <= 140 ? RCED_UNROLL_SMALL : 1;
+#if RCED_PREFETCH
+    // Software pipeline over the input channels: the activation window and the first NPRE
+    // weight words of channel ci+1 are loaded while channel ci is being multiplied, so no
+    // iteration starts by waiting for shared memory.  (Row CIN exists in the slot; what is read
+    // from it is never used.)
+    constexpr int NPRE = NQ < 2 ? NQ : 2;
+    float4 xn[NX4];
+    ulonglong2 wn[NPRE];
+    {
+        const float4* xp = reinterpret_cast<const float4*>(inx);
+#pragma unroll
+        for (int i = 0; i < NX4; ++i) xn[i] = xp[i];
+        const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(W);
+#pragma unroll
+        for (int i = 0; i < NPRE; ++i) wn[i] = wq[i];
+    }
+#else
+    constexpr int NPRE = 0;
+#endif
+#pragma unroll UNR
     for (int ci = 0; ci < CIN; ++ci) {
         float x[NX4 * 4];
-        const float4* xp = reinterpret_cast<const float4*>(inx + ci * kRS);
+#if RCED_PREFETCH
+        ulonglong2 wc[NPRE];
 #pragma unroll
         for (int i = 0; i < NX4; ++i) {
-            const float4 v = xp[i];
-            x[4 * i + 0] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+            x[4 * i + 0] = xn[i].x; x[4 * i + 1] = xn[i].y; x[4 * i + 2] = xn[i].z; x[4 * i + 3] = xn[i].w;
         }
+#pragma unroll
+        for (int i = 0; i < NPRE; ++i) wc[i] = wn[i];
+        {
+            const float4* xp = reinterpret_cast<const float4*>(inx + (ci + 1) * kRS);
+#pragma unroll
+            for (int i = 0; i < NX4; ++i) xn[i] = xp[i];
+        }
+#else
+        {
+            const float4* xp = reinterpret_cast<const float4*>(inx + ci * kRS);
+#pragma unroll
+            for (int i = 0; i < NX4; ++i) {
+                const float4 v = xp[i];
+                x[4 * i + 0] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+            }
+        }
+#endif
         // [kw][CH] weights of this input channel as one flat run of pairs; warp-uniform
         // addresses (broadcast LDS.128 = two pairs), a pair never straddles a 16-byte word
         const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(W + ci * CIB);
@@ -242,24 +295,35 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const int P = k * NP + j;
+#if RCED_PREFETCH
+                const ulonglong2 q = (P >> 1) < NPRE ? wc[(P >> 1) < NPRE ? (P >> 1) : 0] : wq[P >> 1];
+#else
                 const ulonglong2 q = wq[P >> 1];
+#endif
                 const u64 w = (P & 1) ? q.y : q.x;
 #pragma unroll
                 for (int f = 0; f < 4; ++f) fma2_bcast(acc[f][j], x[XB + f + k], w);
             }
         }
-    }
-
-    // ---- tail phase: bin 128, lane == output channel ---------------------------------------
-    {
-        const float* xt = in0 + kRowBin0 + 128 - PADL;   // bins 128-PADL .. 128 (taps beyond hit zeros)
-        const float* wt = W + cl;
-#pragma unroll 2
-        for (int ci = 0; ci < CIN; ++ci) {
+        // bin 128 (lane == output channel): its PADL+1 taps read bins 128-PADL..128; the scalar
+        // FMAs ride in the issue slots the packed FMAs leave free
+#if RCED_TAIL_LDS
+        {
+            const float* xt = in0 + ci * kRS + kRowBin0 + 128 - PADL;   // warp-uniform: broadcast loads
 #pragma unroll
-            for (int k = 0; k <= PADL; ++k)
-                tacc = fmaf(xt[ci * kRS + k], wt[ci * CIB + k * CH], tacc);
+            for (int k = 0; k <= PADL; ++k) tacc = fmaf(xt[k], wt[ci * CIB + k * CH], tacc);
         }
+#else
+#pragma unroll
+        for (int k = 0; k <= PADL; ++k) {   // lane 31 holds those bins in its window
+            const float xs = __shfl_sync(0xffffffffu, x[XB + 4 + k], 31);
+            tacc = fmaf(xs, wt[ci * CIB + k * CH], tacc);
+        }
+#endif
+#if RCED_PREFETCH
+#pragma unroll
+        for (int i = 0; i < NPRE; ++i) wn[i] = wq[NQ + i];   // first words of channel ci+1
+#endif
     }
 
     // ---- epilogue ----------------------------------------------------------------------------
@@ -561,6 +625,9 @@ static cudaError_t launch_net_t(const NetParams& p, int num_sms, cudaStream_t st
 }
 
 cudaError_t launch_net(int arch, bool skip_in_tmem, const NetParams& p, int num_sms, cudaStream_t stream) {
+#ifdef RCED_BENCH_ONLY_V2   // tools/k2_bench.cu: one instantiation keeps experiment builds short
+    return arch == 2 && skip_in_tmem ? launch_net_t<2, true>(p, num_sms, stream) : cudaErrorInvalidValue;
+#else
     switch (arch * 2 + (skip_in_tmem ? 1 : 0)) {
         case 2: return launch_net_t<1, false>(p, num_sms, stream);
         case 3: return launch_net_t<1, true>(p, num_sms, stream);
@@ -570,6 +637,7 @@ cudaError_t launch_net(int arch, bool skip_in_tmem, const NetParams& p, int num_
         case 7: return launch_net_t<3, true>(p, num_sms, stream);
     }
     return cudaErrorInvalidValue;
+#endif
 }
 
 size_t net_smem_bytes_rt(int arch) {

@@ -109,6 +109,66 @@ __global__ void __launch_bounds__(WARPS * 32, 1) probe(float* out, int iters) {
     if (tot == 123.456f) out[0] = tot;
 }
 
+
+// Register-only issue-rate probes: NACC independent accumulator chains per thread.
+template <bool PACKED, int NACC>
+__global__ void __launch_bounds__(1024) peak_probe(float* out, int iters, float a, float b) {
+    float tot = 0.f;
+    if constexpr (PACKED) {
+        float2 acc[NACC];
+        float2 w[4] = {make_float2(a, b), make_float2(b, a), make_float2(a + 1.f, b), make_float2(a, b + 1.f)};
+        float x[4] = {a, b, a + b, a - b};
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = make_float2((float)(threadIdx.x + i), 1.f);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < NACC; ++i) fma2(acc[i], make_float2(x[(i + r) & 3], x[(i + r) & 3]), w[(i >> 2) & 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) tot += acc[i].x + acc[i].y;
+    } else {
+        float acc[NACC];
+        float w[4] = {a, b, a + 1.f, b + 1.f};
+        float x[4] = {a, b, a + b, a - b};
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = (float)(threadIdx.x + i);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < NACC; ++i) acc[i] = fmaf(x[(i + r) & 3], w[(i >> 2) & 3], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) tot += acc[i];
+    }
+    if (tot == 123.456f) out[0] = tot;
+}
+
+template <bool PACKED, int NACC>
+static void run_peak(int warps, int ctas_per_sm, int iters, int sms) {
+    float* d;
+    cudaMalloc(&d, 4);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(a);
+        peak_probe<PACKED, NACC><<<sms * ctas_per_sm, warps * 32>>>(d, iters, 0.999f, 0.001f);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        if (r > 0 && ms < best) best = ms;
+    }
+    const double flop = 2.0 * sms * ctas_per_sm * warps * 32.0 * iters * 8.0 * NACC * (PACKED ? 2 : 1);
+    printf("register-only %s nacc %2d warps/SM %2d : %7.3f ms  %6.2f TFLOP/s (%s)\n", PACKED ? "f32x2 " : "scalar", NACC,
+           warps * ctas_per_sm, best, flop / (best * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+}
+
 template <int COUT, int KW, int CIN, bool PACKED, int WARPS>
 static void run(int iters, int sms) {
     const int warps = WARPS;
@@ -144,6 +204,12 @@ int main() {
     const int sms = p.multiProcessorCount;
     printf("%s, %d SMs\n", p.name, sms);
     const int it = 200;
+    for (int w : {4, 8, 16, 32}) {
+        run_peak<false, 32>(w, 1, 4096, sms);
+        run_peak<true, 32>(w, 1, 4096, sms);
+    }
+    run_peak<false, 16>(8, 8, 4096, sms);
+    run_peak<true, 16>(8, 8, 4096, sms);
     // today's structure: one warp per sub-partition, all channels of the layer
     run<23, 7, 21, false, 4>(it, sms);
     run<23, 7, 21, true, 4>(it, sms);
