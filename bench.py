@@ -158,7 +158,7 @@ def reference_arm(args, rank, world):
     sample = ("each step = %d x 4 s utterances (bounded sample of the 1024-utterance batch), batch %d, %d threads, %s; "
               "stage seconds stft=%.2f network=%.2f rebuild=%.2f" % (per_step, batch, cores, cpu_model(),
                                                                        timings["stft"], timings["network"], timings["rebuild"]))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -167,10 +167,30 @@ def reference_arm(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print on fd 1 (NCCL's version banner, torchrun notices) goes to stderr;
+    the one JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -335,7 +355,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         from oracle import network as onet
         result["cpu_baseline"] = cpu_baseline(pool, onet.random_weights(NET_WORK, seed=0, randomize_bn=False))
-    print(json.dumps(result))
+    emit(result)
     if world > 1:
         dist.destroy_process_group()
 

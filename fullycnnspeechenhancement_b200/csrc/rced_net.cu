@@ -251,15 +251,23 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
     float4 xn[NX4];
     ulonglong2 wn[NPRE];
     {
-        const float4* xp = reinterpret_cast<const float4*>(inx);
-#pragma unroll
-        for (int i = 0; i < NX4; ++i) xn[i] = xp[i];
         const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(W);
 #pragma unroll
         for (int i = 0; i < NPRE; ++i) wn[i] = wq[i];
     }
 #else
     constexpr int NPRE = 0;
+#endif
+    // Everything above (bias / skip pre-load, first weight words) is independent of the layer
+    // input, so it overlaps the partner warp's stores of the previous layer; from here on the
+    // input rows are read.
+    frame_bar(bar_id);   // the previous layer's output (or the staged frame) is complete and visible
+#if RCED_PREFETCH
+    {
+        const float4* xp = reinterpret_cast<const float4*>(inx);
+#pragma unroll
+        for (int i = 0; i < NX4; ++i) xn[i] = xp[i];
+    }
 #endif
 #pragma unroll UNR
     for (int ci = 0; ci < CIN; ++ci) {
@@ -376,7 +384,7 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
         }
     }
     if constexpr (S.save >= 0) sk.wait_st();
-    frame_bar(bar_id);   // the layer output is complete and visible to both warps
+    // no barrier here: the consumer (next layer / final layer) waits right before it reads
 }
 
 // ------------------------------------------------------------------------------------------
@@ -399,6 +407,7 @@ __device__ __forceinline__ void final_layer(const float* __restrict__ sW, float*
     const int c0 = part * CPART;
     const int c1 = c0 + CPART < CIN ? c0 + CPART : CIN;
 
+    frame_bar(bar_id);   // the wide layout written by the last conv layer is complete
     u64 a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;   // (even-tap, odd-tap) partial sums of bins 4l..4l+3
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;     // the unpaired taps
 #pragma unroll 1
@@ -584,8 +593,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
     if (g < p.total_rows) prefetch_frame<ARCH>(p, g, slot, lane, part);
 
     for (; g < p.total_rows; g += stride) {
-        cp_async_wait_all();
-        frame_bar(bar_id);   // input rows and restored halos are visible to both warps
+        cp_async_wait_all();   // this thread's share of the input rows has landed; the first layer's
+                               // barrier makes both shares and the restored halos visible
         run_conv_layers<ARCH, TM, 0>(sW, slot, lane, part, bar_id, sk);
         // the wide layout sits below row SR: the next frame's input can land while the last layer runs
         const long long gn = g + stride;

@@ -1,0 +1,109 @@
+"""BASELINE.json configurations at their full sizes, checked through properties that do not need
+the (slow) CPU oracle on every unit, plus the oracle on a sample of the units.
+
+  configs[0]  R-CED V1, one 4 s utterance, batch 1            -> oracle chain, exact lengths
+  configs[1]  R-CED V2, 1024 x 4 s on one B200                 -> determinism across batch positions,
+                                                                 batch independence, sampled oracle parity
+  configs[2]  CR-CED V3, 4096 ragged 2-8 s utterances          -> exact lengths, batch independence,
+                                                                 sampled oracle parity, chunking invariance
+  configs[3]  1 hour of audio enhanced in chunks               -> equals the un-chunked GPU run, oracle on
+                                                                 windows (the network's receptive field is
+                                                                 8 frames, the IIR forgets after ~1000 samples)
+Tolerances as in test_gpu_parity.py: lengths exact, waveform SNR >= 60 dB against the oracle.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from fullycnnspeechenhancement_b200.engine import Enhancer, num_frames     # noqa: E402
+from fullycnnspeechenhancement_b200.synth import noisy_utterance           # noqa: E402
+from oracle import network, rebuild, stft                                  # noqa: E402
+
+SNR_DB = 60.0
+
+
+def oracle_chain(arch, w, wv):
+    X = stft.compute_spectrogram(wv, 8000, 0.032, 0.016, 256, True).T[None, :, :, None]
+    mag = stft.power_spectrum(X).astype(np.float32)
+    pred = network.forward(arch, w, mag, np.float64).astype(np.float32)
+    return rebuild.rebuild_audio([len(wv)], pred[..., 0], stft.divide_phase(X)[..., 0], 8000, 32.0, 16.0)[0]
+
+
+@pytest.fixture(scope="module")
+def pool():
+    return [noisy_utterance(7000 + i, 32000) for i in range(16)]
+
+
+def test_config0_v1_single_utterance(pool):
+    arch = "FullyCNN"
+    w = network.random_weights(arch, seed=0, randomize_bn=False)     # Glorot, zero bias, BN identity stats
+    eng = Enhancer(arch, w, device=0)
+    out = eng.enhance([pool[0]])[0]
+    eng.close()
+    assert len(out) == 32000 and int(num_frames(32000)) == 249
+    assert rebuild.sdr_db(oracle_chain(arch, w, pool[0]), out) >= SNR_DB
+
+
+def test_config1_v2_1024_utterances(pool):
+    arch = "FullyCNNV2"
+    w = network.random_weights(arch, seed=11, randomize_bn=True)
+    eng = Enhancer(arch, w, device=0)
+    n = 1024
+    waves = [pool[i % len(pool)] for i in range(n)]
+    outs = eng.enhance(waves, chunk_utts=256)
+    assert len(outs) == n and all(len(o) == 32000 for o in outs)
+    assert all(np.isfinite(o).all() for o in outs[::37])
+    # determinism / batch independence: the same waveform gives the same bits wherever it sits in the batch
+    for i in range(len(pool), n, 53):
+        assert np.array_equal(outs[i], outs[i % len(pool)]), i
+    alone = eng.enhance([pool[3]])[0]
+    assert np.array_equal(alone, outs[3])
+    for i in (0, 5, 15):
+        assert rebuild.sdr_db(oracle_chain(arch, w, pool[i]), outs[i]) >= SNR_DB
+    eng.close()
+
+
+def test_config2_v3_4096_ragged():
+    arch = "FullyCNNV3"
+    w = network.random_weights(arch, seed=12, randomize_bn=True)
+    eng = Enhancer(arch, w, device=0)
+    rng = np.random.default_rng(2)
+    n = 4096
+    lengths = rng.integers(16000, 64001, n)                      # 2-8 s, voicebank-shaped
+    base = [noisy_utterance(8000 + i, 64000) for i in range(8)]
+    waves = [base[i % 8][:L] for i, L in enumerate(lengths)]
+    outs = eng.enhance(waves, chunk_utts=512)
+    assert [len(o) for o in outs] == [int(L) for L in lengths]
+    # chunking must not matter, and neither must the batch mates
+    again = eng.enhance(waves[100:140], chunk_utts=7)
+    for a, b in zip(again, outs[100:140]):
+        assert np.array_equal(a, b)
+    for i in (0, 1234, 4095):
+        assert rebuild.sdr_db(oracle_chain(arch, w, waves[i]), outs[i]) >= SNR_DB
+    eng.close()
+
+
+def test_config3_one_hour_stream():
+    arch = "FullyCNNV2"
+    w = network.random_weights(arch, seed=13, randomize_bn=True)
+    eng = Enhancer(arch, w, device=0)
+    L = 8000 * 3600
+    minute = noisy_utterance(9000, 8000 * 60)
+    # an hour made of a repeated minute with a slow gain drift, so that no two chunks are equal
+    gain = np.linspace(0.5, 1.0, 60, dtype=np.float32)
+    wv = np.concatenate([minute * g for g in gain])
+    assert len(wv) == L and int(num_frames(L)) == 224999
+    whole = eng.enhance([wv])[0]
+    chunked = eng.enhance_stream(wv, chunk_seconds=4.0)
+    assert len(whole) == L and len(chunked) == L
+    assert rebuild.sdr_db(whole, chunked) >= 100.0                # continuity at every chunk join
+    # oracle on windows: 13 segments of look-back, 6 of look-ahead make a window's interior exact
+    for start in (0, 8000 * 1800 + 128 * 5, L - 8000 * 6):
+        a = max(0, start - 13 * 128)
+        b = min(L, start + 8000 * 4 + 6 * 128)
+        ref = oracle_chain(arch, w, wv[a:b])
+        k0, k1 = start - a, min(start + 8000 * 4, L) - a
+        assert rebuild.sdr_db(ref[k0:k1], whole[start:start + (k1 - k0)]) >= SNR_DB, start
+    eng.close()
