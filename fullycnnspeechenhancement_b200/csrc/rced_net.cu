@@ -229,25 +229,19 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
     }
 
     // ---- main phase: bins 4l..4l+3, this warp's channel pairs -------------------------------
-    constexpr int NQ = CIB / 4;                        // 16-byte weight words per input channel
-    const float* wt = W + cl;                          // bin-128 phase: this lane's channel
-#ifndef RCED_PREFETCH
-#define RCED_PREFETCH 1
-#endif
-#ifndef RCED_UNROLL_SMALL
-#define RCED_UNROLL_SMALL 2
-#endif
-#ifndef RCED_TAIL_LDS
-#define RCED_TAIL_LDS 0
-#endif
-    constexpr int BODY = KW * NP * 4;                  // packed FMAs per input channel
-    constexpr int UNR = BODY <= 140 ? RCED_UNROLL_SMALL : 1;
-#if RCED_PREFETCH
     // Software pipeline over the input channels: the activation window and the first NPRE
-    // weight words of channel ci+1 are loaded while channel ci is being multiplied, so no
-    // iteration starts by waiting for shared memory.  (Row CIN exists in the slot; what is read
-    // from it is never used.)
+    // weight words of channel ci+1 are loaded while channel ci is being multiplied.  (Row CIN
+    // exists in the slot; what is read from it is never used.)  Loop bodies of up to 140 packed
+    // FMAs are unrolled twice; larger unrolls lose to the instruction cache.  Measured and
+    // dropped (tools/k2_bench.cu): no prefetch (-0.5 %), deeper weight prefetch, f-outer loop
+    // order (ptxas re-schedules the packed FMAs into weight-reuse order whatever the source says),
+    // broadcast LDS instead of SHFL for bin 128, holding part 1 back to de-phase the two warps
+    // (all within +-1 %), unroll 3 / 4 (-8 % / -11 %).
+    constexpr int NQ = CIB / 4;                        // 16-byte weight words per input channel
     constexpr int NPRE = NQ < 2 ? NQ : 2;
+    constexpr int BODY = KW * NP * 4;                  // packed FMAs per input channel
+    constexpr int UNR = BODY <= 140 ? 2 : 1;
+    const float* wt = W + cl;                          // bin-128 phase: this lane's channel
     float4 xn[NX4];
     ulonglong2 wn[NPRE];
     {
@@ -255,24 +249,18 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
 #pragma unroll
         for (int i = 0; i < NPRE; ++i) wn[i] = wq[i];
     }
-#else
-    constexpr int NPRE = 0;
-#endif
     // Everything above (bias / skip pre-load, first weight words) is independent of the layer
     // input, so it overlaps the partner warp's stores of the previous layer; from here on the
     // input rows are read.
     frame_bar(bar_id);   // the previous layer's output (or the staged frame) is complete and visible
-#if RCED_PREFETCH
     {
         const float4* xp = reinterpret_cast<const float4*>(inx);
 #pragma unroll
         for (int i = 0; i < NX4; ++i) xn[i] = xp[i];
     }
-#endif
 #pragma unroll UNR
     for (int ci = 0; ci < CIN; ++ci) {
         float x[NX4 * 4];
-#if RCED_PREFETCH
         ulonglong2 wc[NPRE];
 #pragma unroll
         for (int i = 0; i < NX4; ++i) {
@@ -285,16 +273,6 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
 #pragma unroll
             for (int i = 0; i < NX4; ++i) xn[i] = xp[i];
         }
-#else
-        {
-            const float4* xp = reinterpret_cast<const float4*>(inx + ci * kRS);
-#pragma unroll
-            for (int i = 0; i < NX4; ++i) {
-                const float4 v = xp[i];
-                x[4 * i + 0] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-            }
-        }
-#endif
         // [kw][CH] weights of this input channel as one flat run of pairs; warp-uniform
         // addresses (broadcast LDS.128 = two pairs), a pair never straddles a 16-byte word
         const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(W + ci * CIB);
@@ -303,35 +281,21 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ sW, float* 
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const int P = k * NP + j;
-#if RCED_PREFETCH
                 const ulonglong2 q = (P >> 1) < NPRE ? wc[(P >> 1) < NPRE ? (P >> 1) : 0] : wq[P >> 1];
-#else
-                const ulonglong2 q = wq[P >> 1];
-#endif
                 const u64 w = (P & 1) ? q.y : q.x;
 #pragma unroll
                 for (int f = 0; f < 4; ++f) fma2_bcast(acc[f][j], x[XB + f + k], w);
             }
         }
-        // bin 128 (lane == output channel): its PADL+1 taps read bins 128-PADL..128; the scalar
-        // FMAs ride in the issue slots the packed FMAs leave free
-#if RCED_TAIL_LDS
-        {
-            const float* xt = in0 + ci * kRS + kRowBin0 + 128 - PADL;   // warp-uniform: broadcast loads
+        // bin 128 (lane == output channel): its PADL+1 taps read bins 128-PADL..128, which lane 31
+        // holds in its window; the scalar FMAs ride in the issue slots the packed FMAs leave free
 #pragma unroll
-            for (int k = 0; k <= PADL; ++k) tacc = fmaf(xt[k], wt[ci * CIB + k * CH], tacc);
-        }
-#else
-#pragma unroll
-        for (int k = 0; k <= PADL; ++k) {   // lane 31 holds those bins in its window
+        for (int k = 0; k <= PADL; ++k) {
             const float xs = __shfl_sync(0xffffffffu, x[XB + 4 + k], 31);
             tacc = fmaf(xs, wt[ci * CIB + k * CH], tacc);
         }
-#endif
-#if RCED_PREFETCH
 #pragma unroll
         for (int i = 0; i < NPRE; ++i) wn[i] = wq[NQ + i];   // first words of channel ci+1
-#endif
     }
 
     // ---- epilogue ----------------------------------------------------------------------------
