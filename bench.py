@@ -30,6 +30,7 @@ SAMPLE_RATE = 8000
 POOL = 64                    # distinct synthetic utterances, tiled to N_UTT
 METRIC = "R-CED V2 audio-seconds enhanced per second"
 UNIT = "audio-s/s"
+DEFAULT_VARIANT = "ffma"     # network kernel timed by default
 
 
 def synth_pool():
@@ -198,6 +199,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-in-global", action="store_true", help="park skips in global scratch instead of TMEM")
+    ap.add_argument("--variant", default=DEFAULT_VARIANT, choices=["ffma", "tc"],
+                    help="network kernel: FP32 FFMA, or tcgen05 tensor cores with the FP16 x3 split")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -228,6 +231,7 @@ def main():
     eng = Enhancer(NET_WORK, weights, device=local_rank)
     if args.skip_in_global:
         eng.set_skip_in_tmem(False)
+    eng.set_variant(args.variant)
 
     pool = synth_pool()
     lengths = np.full(N_UTT, UTT_SAMPLES, dtype=np.int64)

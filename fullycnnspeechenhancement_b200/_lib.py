@@ -8,7 +8,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librced_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
+VARIANT_FFMA = 0   # FP32 FFMA network kernel
+VARIANT_TC = 1     # tcgen05 tensor-core kernel (FP16 x3 split)
 
 c_i64 = ctypes.c_int64
 c_i32 = ctypes.c_int32
@@ -31,6 +33,13 @@ SIGNATURES = {
     "rced_arch": (ctypes.c_int, [c_p]),
     "rced_device": (ctypes.c_int, [c_p]),
     "rced_set_skip_in_tmem": (ctypes.c_int, [c_p, ctypes.c_int]),
+    "rced_set_variant": (ctypes.c_int, [c_p, ctypes.c_int]),
+    "rced_variant": (ctypes.c_int, [c_p]),
+    "rced_tc_status": (ctypes.c_int, [c_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint)]),
+    "rced_tc_image_bytes": (c_i64, [ctypes.c_int]),
+    "rced_tc_bias_count": (c_i64, [ctypes.c_int]),
+    "rced_tc_pack_weights": (ctypes.c_int, [ctypes.c_int, c_p, ctypes.c_size_t, c_p, ctypes.c_size_t, c_p, ctypes.c_size_t]),
+    "rced_tc_layout": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_i64), ctypes.c_int]),
     "rced_stft": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, ctypes.c_int, c_i64, c_p, c_p, c_p]),
     "rced_forward": (ctypes.c_int, [c_p, c_p, c_p, ctypes.c_int, c_i64, c_p, c_p]),
     "rced_istft": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, c_i64, ctypes.c_int, c_p, c_p, c_p, c_p]),

@@ -11,6 +11,7 @@
 #include "../../include/rced.h"
 #include "rced_arch.cuh"
 #include "rced_internal.h"
+#include "rced_tc.cuh"
 
 namespace rced {
 
@@ -200,6 +201,13 @@ struct rced_handle {
     bool skip_in_tmem;
     float* d_packed;
     float* d_scratch;
+    // tensor-core variant (rced_net_tc.cu), allocated by rced_set_variant(h, RCED_VARIANT_TC)
+    int variant;
+    std::vector<float> folded;
+    unsigned char* d_tc_img;
+    float* d_tc_bias;
+    float* d_tc_skip;
+    unsigned int* d_tc_flags;
 };
 
 struct DeviceGuard {
@@ -216,7 +224,7 @@ struct DeviceGuard {
 
 extern "C" {
 
-int rced_abi_version(void) { return 1; }
+int rced_abi_version(void) { return 2; }
 const char* rced_last_error(void) { return t_err.c_str(); }
 
 int64_t rced_num_frames(int64_t n) {
@@ -299,6 +307,12 @@ int rced_create(int arch, const float* folded, size_t n_folded, int device, rced
     h->skip_in_tmem = true;
     h->d_packed = nullptr;
     h->d_scratch = nullptr;
+    h->variant = RCED_VARIANT_FFMA;
+    h->folded.assign(folded, folded + n_folded);
+    h->d_tc_img = nullptr;
+    h->d_tc_bias = nullptr;
+    h->d_tc_skip = nullptr;
+    h->d_tc_flags = nullptr;
     if ((e = cudaMalloc(&h->d_packed, packed.size() * sizeof(float))) != cudaSuccess) {
         delete h;
         return cuda_fail(e, "cudaMalloc(weights)");
@@ -317,6 +331,10 @@ void rced_destroy(rced_handle* h) {
     DeviceGuard guard(h->device);
     if (h->d_packed) cudaFree(h->d_packed);
     if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_tc_img) cudaFree(h->d_tc_img);
+    if (h->d_tc_bias) cudaFree(h->d_tc_bias);
+    if (h->d_tc_skip) cudaFree(h->d_tc_skip);
+    if (h->d_tc_flags) cudaFree(h->d_tc_flags);
     delete h;
 }
 
@@ -332,6 +350,92 @@ int rced_set_skip_in_tmem(rced_handle* h, int enable) {
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(skip scratch)");
     }
     h->skip_in_tmem = enable != 0;
+    return RCED_OK;
+}
+
+int64_t rced_tc_image_bytes(int arch) { return arch_ok(arch) ? tc_image_bytes(arch) : -1; }
+int64_t rced_tc_bias_count(int arch) { return arch_ok(arch) ? tc_bias_floats(arch) : -1; }
+int rced_tc_pack_weights(int arch, const float* folded, size_t n_folded, void* image, size_t image_bytes, float* bias,
+                         size_t n_bias) {
+    if (!arch_ok(arch)) return fail(RCED_ERR_ARG, "unknown arch");
+    if (!folded || !image || !bias) return fail(RCED_ERR_ARG, "null pointer");
+    if ((int64_t)n_folded != folded_count(arch)) return fail(RCED_ERR_ARG, "folded weight count mismatch");
+    if ((int64_t)image_bytes != tc_image_bytes(arch) || (int64_t)n_bias != tc_bias_floats(arch))
+        return fail(RCED_ERR_ARG, "image / bias size mismatch");
+    tc_pack_weights(arch, folded, static_cast<unsigned char*>(image), bias);
+    return RCED_OK;
+}
+int rced_tc_layout(int arch, int64_t* out, int n) {
+    if (!arch_ok(arch) || !out) return fail(RCED_ERR_ARG, "bad argument");
+    const int ns = tc::n_steps(arch), nu = tc::total_units(arch);
+    if (n < 12 + 6 * ns + 2 * nu) return fail(RCED_ERR_ARG, "output too small");
+    out[0] = ns;
+    out[1] = nu;
+    out[2] = tc::w_image_bytes(arch);
+    out[3] = tc::smem_total(arch);
+    out[4] = tc::kPlane16;
+    out[5] = tc::kLead;
+    out[6] = tc::kFS;
+    out[7] = tc::kFB;
+    out[8] = tc::kTiles;
+    out[9] = tc::kLo16;
+    out[10] = tc::kFinalTaps;
+    out[11] = (int64_t)tc::skip_floats_per_cta(arch);
+    for (int s = 0; s < ns; ++s) {
+        int64_t* o = out + 12 + 6 * s;
+        o[0] = tc::step_units(arch, s);
+        o[1] = tc::unit_base(arch, s);
+        o[2] = tc::step_np(arch, s);
+        o[3] = tc::step_tile_bytes(arch, s);
+        o[4] = tc::step_w_off(arch, s);
+        o[5] = tc::is_final(arch, s) ? 1 : 0;
+    }
+    int64_t* u = out + 12 + 6 * ns;
+    for (int s = 0; s < ns; ++s)
+        for (int i = 0; i < tc::step_units(arch, s); ++i) {
+            const int o0 = tc::chunk_off16(arch, s, 2 * i);
+            const int o1 = 2 * i + 1 < tc::step_chunks(arch, s) ? tc::chunk_off16(arch, s, 2 * i + 1) : o0 + 1;
+            u[2 * (tc::unit_base(arch, s) + i)] = o0;
+            u[2 * (tc::unit_base(arch, s) + i) + 1] = o1 - o0;
+        }
+    return RCED_OK;
+}
+
+int rced_set_variant(rced_handle* h, int variant) {
+    if (!h) return fail(RCED_ERR_ARG, "null handle");
+    if (variant != RCED_VARIANT_FFMA && variant != RCED_VARIANT_TC) return fail(RCED_ERR_ARG, "unknown variant");
+    if (variant == RCED_VARIANT_TC && !h->d_tc_img) {
+        for (float w : h->folded)
+            if (!(fabsf(w) <= 65504.f)) return fail(RCED_ERR_STATE, "a folded weight exceeds the FP16 range: tensor-core variant refused");
+        DeviceGuard guard(h->device);
+        std::vector<unsigned char> img((size_t)tc_image_bytes(h->arch));
+        std::vector<float> bias((size_t)tc_bias_floats(h->arch));
+        tc_pack_weights(h->arch, h->folded.data(), img.data(), bias.data());
+        const size_t skip_bytes = (size_t)h->num_sms * tc_skip_floats_per_cta(h->arch) * sizeof(float);
+        cudaError_t e;
+        if ((e = cudaMalloc(&h->d_tc_img, img.size())) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc image)");
+        if ((e = cudaMalloc(&h->d_tc_bias, bias.size() * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc bias)");
+        if ((e = cudaMalloc(&h->d_tc_skip, skip_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc skip scratch)");
+        if ((e = cudaMalloc(&h->d_tc_flags, 2 * sizeof(unsigned int))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc flags)");
+        if ((e = cudaMemcpy(h->d_tc_img, img.data(), img.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tc image)");
+        if ((e = cudaMemcpy(h->d_tc_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return cuda_fail(e, "cudaMemcpy(tc bias)");
+        if ((e = cudaMemset(h->d_tc_skip, 0, skip_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMemset(tc skip scratch)");
+        if ((e = cudaMemset(h->d_tc_flags, 0, 2 * sizeof(unsigned int))) != cudaSuccess) return cuda_fail(e, "cudaMemset(tc flags)");
+    }
+    h->variant = variant;
+    return RCED_OK;
+}
+int rced_variant(const rced_handle* h) { return h ? h->variant : -1; }
+int rced_tc_status(rced_handle* h, float* max_abs, unsigned int* protocol_error) {
+    if (!h) return fail(RCED_ERR_ARG, "null handle");
+    if (!h->d_tc_flags) return fail(RCED_ERR_STATE, "tensor-core variant was never selected");
+    DeviceGuard guard(h->device);
+    unsigned int f[2];
+    cudaError_t e = cudaMemcpy(f, h->d_tc_flags, sizeof(f), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tc flags)");
+    if (max_abs) memcpy(max_abs, &f[0], 4);
+    if (protocol_error) *protocol_error = f[1];
     return RCED_OK;
 }
 
@@ -371,7 +475,20 @@ int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n
     p.n_utt = n_utt;
     p.total_rows = total_rows;
     p.skip_scratch = h->d_scratch;
-    cudaError_t e = launch_net(h->arch, h->skip_in_tmem, p, h->num_sms, (cudaStream_t)stream);
+    p.guard = nullptr;
+    cudaError_t e;
+    if (h->variant == RCED_VARIANT_TC) {
+        // tensor-core kernel first; the FP32 FFMA kernel follows on the same stream and returns at
+        // once unless the range guard tripped (an activation beyond the FP16 range) or the
+        // tensor-core kernel reported a protocol error -- stream-ordered, no host synchronisation
+        if ((e = cudaMemsetAsync(h->d_tc_flags, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream)) != cudaSuccess)
+            return cuda_fail(e, "cudaMemsetAsync(tc flags)");
+        e = launch_net_tc(h->arch, p, h->d_tc_img, h->d_tc_bias, h->d_tc_skip, h->d_tc_flags, h->num_sms, (cudaStream_t)stream);
+        count_launch();
+        if (e != cudaSuccess) return cuda_fail(e, "rced_forward launch (tensor-core variant)");
+        p.guard = h->d_tc_flags;
+    }
+    e = launch_net(h->arch, h->skip_in_tmem, p, h->num_sms, (cudaStream_t)stream);
     count_launch();
     return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_forward launch");
 }

@@ -14,6 +14,11 @@ struct NetParams {
     int n_utt;
     long long total_rows;
     float* skip_scratch;        // only read when skips are not parked in tensor memory
+    // When not null: flags written by the tensor-core kernel that ran before on the same stream
+    // ([0] bits of the largest |activation| it stored as FP16, [1] protocol error).  The FFMA
+    // kernel then only runs (and overwrites `out`) if the FP16 range was exceeded or an error
+    // was reported.
+    const unsigned int* guard;
 };
 
 struct StftParams {
@@ -41,6 +46,14 @@ struct IstftParams {
 
 cudaError_t launch_net(int arch, bool skip_in_tmem, const NetParams& p, int num_sms, cudaStream_t stream);
 size_t net_smem_bytes_rt(int arch);
+// tensor-core variant (rced_net_tc.cu)
+int tc_image_bytes(int arch);
+int tc_bias_floats(int arch);
+size_t tc_skip_floats_per_cta(int arch);
+int tc_smem_bytes(int arch);
+void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* bias);
+cudaError_t launch_net_tc(int arch, const NetParams& p, const unsigned char* wimg, const float* bias, float* skip,
+                          unsigned int* flags, int num_sms, cudaStream_t stream);
 cudaError_t launch_stft(const StftParams& p, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, long long max_rows_per_utt, cudaStream_t stream);
 cudaError_t upload_tables_stft();    // twiddles + window tables of K1 -> current device

@@ -512,6 +512,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_tmem;
 
+    // fall-back role behind the tensor-core variant: nothing to do unless its guard tripped
+    if (p.guard != nullptr && p.guard[0] <= 0x477FE000u /* 65504.0f */ && p.guard[1] == 0u) return;
+
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int fs = warp & (kFramesPerCta - 1);   // frame slot == SM sub-partition == tensor-memory lane quadrant

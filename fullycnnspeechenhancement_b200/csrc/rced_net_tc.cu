@@ -1,0 +1,631 @@
+// K2-TC: tensor-core variant of the fused R-CED / CR-CED network kernel (sm_100a, tcgen05).
+//
+// Same contract as rced_net_kernel (rced_net.cu): replaces FullyCNNTester.test_step /
+// sess.run(pred) of the reference (model_utils/tester.py:85-90) for the graphs of
+// model_utils/model.py, one fused kernel, activations never leave the SM.
+//
+// Design (rced_tc.cuh):
+//  * a CTA takes a batch of 7 consecutive spectrogram frames through all layers.  The (frame, bin)
+//    rows are flattened with a stride of 136 rows per frame, so that the 7 zero rows between two
+//    frames are the SAME-padding halo of both; 8 row tiles of M = 128 cover the batch;
+//  * every conv layer is an implicit GEMM without im2col: D[row][cout] += A_tap[row][cin] *
+//    W_tap[cout][cin], one tcgen05.mma (kind::f16, K = 16) per pair of (tap, 8-channel group)
+//    chunks, the A descriptor of a tap being the activation plane shifted by (tap - pad) rows;
+//  * FP32 accuracy from FP16 tensor cores by an error-compensated split: activations and
+//    weights are stored as hi + lo FP16 pairs and every K step issues A_hi x [Whi | Wlo]
+//    (N = 2 NP) and A_lo x Whi (N = NP) into FP32 accumulators in tensor memory;
+//  * warp roles: warp 0 issues the MMAs (one elected lane), warp 1 streams the next layer's
+//    weight tiles from L2 with bulk async copies into a double buffer, warps 4-11 are two
+//    epilogue groups (tcgen05.ld -> bias, skip, ReLU -> hi/lo split -> st.shared of the next
+//    layer's planes).  Layers overlap tile by tile: the epilogue of (layer, tile t) starts when
+//    the MMAs of tile t+1 have completed (they read tile t's halo rows, planes are updated in
+//    place) and the MMAs of (layer+1, t) start when the epilogues of tiles t-1..t+1 are done;
+//  * the (1,129) output layer runs "taps in N": D[row][tap] = A[row][cin] * Wf[tap][cin] in three
+//    passes of 48 taps; the epilogue adds D[row b][tap j] into out[b - j + 64] of the row's frame
+//    (a shuffle-skewed diagonal sum per warp, fixed order) -- no 64-row halo is ever materialised;
+//  * skip tensors go to a per-CTA FP32 scratch in global memory (L2 resident);
+//  * range guard: FP16 overflows beyond 65504.  The kernel records the largest |activation| it
+//    stored; rced_forward re-runs the batch with the FP32 FFMA kernel when the guard tripped.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "rced_internal.h"
+#include "rced_tc.cuh"
+
+namespace rced {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol error must end the kernel with an error flag, not hang the GPU.  Once
+// any wait has timed out every other wait of the grid gives up at its next check of the flag.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err, int code) {
+    for (int it = 0; it < (1 << 21); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((it & 255) == 255 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) return;
+    }
+    atomicMax(err, (unsigned int)code);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers written by tcgen05.ld may only be read after tcgen05.wait::ld (see rced_net.cu)
+__device__ __forceinline__ void reg_fence8(float (&v)[8]) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (version 1): start and LBO in the low word,
+// SBO = 128 bytes (rows of an 8-row group are 16 bytes apart, groups follow each other) in the high
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
+// instruction descriptor: FP16 A/B (format 0), FP32 accumulate, both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// x = hi + lo as two FP16 pairs; element a goes to the low half
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void store_split8(unsigned char* act, int cg, int q, const float (&v)[8]) {
+    uint4 h, l;
+    split2(v[0], v[1], h.x, l.x);
+    split2(v[2], v[3], h.y, l.y);
+    split2(v[4], v[5], h.z, l.z);
+    split2(v[6], v[7], h.w, l.w);
+    uint4* ph = reinterpret_cast<uint4*>(act) + cg * kPlane16 + q;
+    ph[0] = h;
+    ph[kLo16] = l;
+}
+
+struct TcParams {
+    const unsigned char* wimg;   // weight image (global): per step, per unit, [2][rows][8] halfs
+    const float* bias;           // [n_steps][32]
+    const float* in;             // mag  [total_rows][129]
+    float* out;                  // pred [total_rows][129]
+    const long long* row_off;    // [n_utt + 1]
+    int n_utt;
+    long long total_rows;
+    float* skip;                 // per-CTA scratch for the skip tensors
+    unsigned int* flags;         // [0] bits of the largest |activation| stored as FP16, [1] protocol error
+};
+
+struct Ctx {
+    unsigned char* smem;
+    unsigned char* act;
+    uint32_t bars;      // shared address of the barrier block
+    uint32_t tm;        // tensor-memory base
+    const float* bias;  // shared copy
+    const long long* bnd;
+    unsigned int* err;
+    int lane, quad, grp, et, nf;
+    float* skip;
+    float* priv;        // this warp's row-space accumulator of the (1,129) layer [kRows]
+    long long g0;
+};
+
+__device__ __forceinline__ uint32_t bar_addr(const Ctx& c, int slot) { return c.bars + 8u * slot; }
+
+// utterance [lo, hi) that owns global row g
+__device__ __forceinline__ void locate(const long long* __restrict__ row_off, int n_utt, long long g, long long& lo, long long& hi) {
+    int a = 0, b = n_utt;
+    while (b - a > 1) {
+        const int m = (a + b) >> 1;
+        if (__ldg(row_off + m) <= g) a = m; else b = m;
+    }
+    lo = __ldg(row_off + a);
+    hi = __ldg(row_off + a + 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogue of one conv layer for one row tile
+// ------------------------------------------------------------------------------------------
+template <int ARCH, int LI>
+__device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int t, const uint32_t par, float& amax) {
+    constexpr LSpec S = spec(ARCH, LI);
+    constexpr int NP = step_np(ARCH, LI);
+    constexpr int CG = (S.cout + 7) / 8;
+    constexpr bool PRE = S.add >= 0 && !S.after;
+    constexpr bool POST = S.add >= 0 && S.after;
+    constexpr bool SAVE = S.save >= 0;
+
+    const int r = t * 128 + c.quad * 32 + c.lane;   // row in tile space
+    const int fi = r / kFS, b = r - fi * kFS;
+    const bool valid = fi < c.nf && b < kBins;
+    const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
+
+    // the skip tensor (this thread's own row, written by this thread layers ago) does not depend
+    // on the accumulator: its L2 latency hides behind the wait for the MMAs
+    float4 sk[CG][2];
+#pragma unroll
+    for (int g = 0; g < CG; ++g) sk[g][0] = sk[g][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (S.add >= 0) {
+        const float4* sp = reinterpret_cast<const float4*>(c.skip) + ((size_t)skip_c8_base(ARCH, S.add >= 0 ? S.add : 0) * kRows + r) * 2;
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+            sk[g][0] = sp[(size_t)g * kRows * 2];
+            sk[g][1] = sp[(size_t)g * kRows * 2 + 1];
+        }
+    }
+
+    // accumulator of this tile complete; MMAs of the next tile (which read this tile's last rows
+    // as their halo) complete as well, so the planes can be overwritten in place
+    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 100 + LI);
+    if (t + 1 < kTiles) mbar_wait(bar_addr(c, kBarAccFull + t + 1), par, c.err, 200 + LI);
+    fence_after();
+
+    float d1[CG][8], d2[CG][8];
+#pragma unroll
+    for (int g = 0; g < CG; ++g) {
+        tmem_ld8(ta + g * 8, d1[g]);
+        tmem_ld8(ta + NP + g * 8, d2[g]);
+    }
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < CG; ++g) {
+        reg_fence8(d1[g]);
+        reg_fence8(d2[g]);
+    }
+    const float* bias = c.bias + LI * 32;
+#pragma unroll
+    for (int g = 0; g < CG; ++g) {
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + g * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float ss[8] = {sk[g][0].x, sk[g][0].y, sk[g][0].z, sk[g][0].w, sk[g][1].x, sk[g][1].y, sk[g][1].z, sk[g][1].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = (d1[g][e] + d2[g][e]) + bb[e];
+            if constexpr (PRE) x += ss[e];
+            if constexpr (S.relu) x = fmaxf(x, 0.f);
+            if constexpr (POST) x += ss[e];
+            x = valid ? x : 0.f;
+            amax = fmaxf(amax, fabsf(x));
+            v[e] = x;
+        }
+        if constexpr (SAVE) {
+            float4* dp = reinterpret_cast<float4*>(c.skip) + ((size_t)(skip_c8_base(ARCH, S.save >= 0 ? S.save : 0) + g) * kRows + r) * 2;
+            dp[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dp[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        store_split8(c.act, g, kLead + r, v);
+    }
+    fence_before();       // tcgen05.ld of this accumulator ordered before the barrier
+    fence_async_smem();   // plane writes visible to the tensor core (async proxy)
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(bar_addr(c, kBarActReady + t));
+}
+
+// Epilogue of one pass of the (1,129) layer for one row tile.  D[row r][tap] belongs to output
+// row r - tap + 64 (same frame only): the warp sums its 32 x 48 block along the diagonals with one
+// shuffle per tap -- lane m collects the diagonals d = tap - lane in {m - 32, m, m + 32} -- and adds
+// the three sums to its private row-space accumulator (no atomics, fixed summation order).
+template <int ARCH, int PASS>
+__device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const uint32_t par) {
+    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 300 + PASS);
+    fence_after();
+    const int r0 = t * 128 + c.quad * 32;
+    const int r = r0 + c.lane;
+    const int fi = r / kFS, b = r - fi * kFS;
+    const bool valid = fi < c.nf && b < kBins;
+    const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
+    float d[kFinalTaps / 8][8];
+#pragma unroll
+    for (int g = 0; g < kFinalTaps / 8; ++g) tmem_ld8(ta + g * 8, d[g]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < kFinalTaps / 8; ++g) reg_fence8(d[g]);
+    // tap = 48 PASS + i stays inside the frame iff 0 <= b - tap + 64 <= 128
+    const int ilo = valid ? b - 64 - PASS * kFinalTaps : 4096;
+    float am = 0.f, a0 = 0.f, ap = 0.f;
+#pragma unroll
+    for (int g = 0; g < kFinalTaps / 8; ++g)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = g * 8 + e;
+            const float v = (unsigned)(i - ilo) <= 128u ? d[g][e] : 0.f;
+            const float x = __shfl_sync(0xffffffffu, v, (i - c.lane) & 31);   // from lane l = (i - m) mod 32
+            if (i < 32) {
+                if (c.lane <= i) a0 += x; else am += x;        // d = m  |  d = m - 32
+            } else {
+                if (c.lane <= i - 32) ap += x; else a0 += x;   // d = m + 32  |  d = m
+            }
+        }
+    // output row of diagonal d: r0 + 64 - 48 PASS - d
+    float* pw = c.priv;
+    const int ro = r0 + 64 - PASS * kFinalTaps - c.lane;
+    if (ro + 32 >= 0 && ro + 32 < kRows) pw[ro + 32] += am;
+    if (ro >= 0 && ro < kRows) pw[ro] += a0;
+    if (ro - 32 >= 0 && ro - 32 < kRows) pw[ro - 32] += ap;
+    fence_before();
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(bar_addr(c, kBarActReady + t));
+}
+
+template <int ARCH, int STEP>
+__device__ __forceinline__ void epi_steps(const Ctx& c, const uint32_t k0, float& amax) {
+    if constexpr (STEP < n_steps(ARCH)) {
+        const uint32_t par = (k0 + STEP) & 1;
+        if constexpr (STEP == num_layers(ARCH) - 1) {
+            // planes 2 and 3 are dead once the MMAs of the last conv layer have completed (both
+            // groups have seen acc_full of its last tile: group 0 as the halo condition of tile 6,
+            // group 1 for tile 7): they now hold the per-warp accumulators of the output layer
+            for (int i = c.lane; i < kRows / 4; i += 32) reinterpret_cast<float4*>(c.priv)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+        }
+#pragma unroll 1
+        for (int t = c.grp; t < kTiles; t += 2) {
+            if constexpr (is_final(ARCH, STEP)) epi_final_tile<ARCH, STEP - (num_layers(ARCH) - 1)>(c, t, par);
+            else epi_conv_tile<ARCH, STEP>(c, t, par, amax);
+        }
+        epi_steps<ARCH, STEP + 1>(c, k0, amax);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int ARCH>
+__global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int NS = n_steps(ARCH);
+    constexpr int NL = num_layers(ARCH);
+    __shared__ uint32_t s_tmem;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char* act = smem;
+    int2* tab = reinterpret_cast<int2*>(smem + smem_tab_off(ARCH));
+    int4* steps = reinterpret_cast<int4*>(smem + smem_step_off(ARCH));
+    float* s_bias = reinterpret_cast<float*>(smem + smem_bias_off(ARCH));
+    long long* bnd = reinterpret_cast<long long*>(smem + smem_bnd_off(ARCH));
+    const uint32_t bars = smem_u32(smem + smem_bar_off(ARCH));
+    unsigned int* err = p.flags + 1;
+
+    // ---- one-time setup ----------------------------------------------------------------------
+    for (int i = threadIdx.x; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NS * 32; i += kThreads) s_bias[i] = p.bias[i];
+    for (int s = 0; s < NS; ++s) {
+        const int nu = step_units(ARCH, s), nc = step_chunks(ARCH, s), ub = unit_base(ARCH, s);
+        for (int u = threadIdx.x; u < nu; u += kThreads) {
+            const int o0 = chunk_off16(ARCH, s, 2 * u);
+            const int o1 = 2 * u + 1 < nc ? chunk_off16(ARCH, s, 2 * u + 1) : o0 + 1;   // dummy chunk: zero weights
+            tab[ub + u] = make_int2(o0, o1 - o0);
+        }
+        if (threadIdx.x == 0)
+            steps[s] = make_int4(nu, ub, step_np(ARCH, s), (step_tile_bytes(ARCH, s) >> 4) | (is_final(ARCH, s) ? (1 << 16) : 0));
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kTiles; ++i) {
+            mbar_init(bars + 8 * (kBarAccFull + i), 1);
+            mbar_init(bars + 8 * (kBarActReady + i), 4);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bars + 8 * (kBarWFull + i), 1);
+            mbar_init(bars + 8 * (kBarWFree + i), 1);
+        }
+        mbar_init(bars + 8 * kBarInReady, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tm = s_tmem;
+    const long long NB = (p.total_rows + kFB - 1) / kFB;
+
+    if (warp == 0) {
+        // ================= MMA issue =================
+        const uint32_t act16 = smem_u32(act) >> 4;
+        uint32_t it = 0;
+        for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
+            mbar_wait(bars + 8 * kBarInReady, it & 1, err, 1);
+#pragma unroll 1
+            for (int s = 0; s < NS; ++s) {
+                const uint32_t k = it * NS + s;
+                const int wb = k & 1;
+                mbar_wait(bars + 8 * (kBarWFull + wb), (k >> 1) & 1, err, 2);
+                const int4 st = steps[s];
+                const int nu = st.x, np = st.z, tile16 = st.w & 0xFFFF;
+                const bool fin = (st.w >> 16) != 0;
+                const int2* ut = tab + st.y;
+                const uint32_t w16 = smem_u32(smem + smem_w_off(ARCH, wb)) >> 4;
+                const uint32_t id_a = idesc_f16(fin ? np : 2 * np), id_b = idesc_f16(np);
+                const uint32_t b_lbo = (uint32_t)(2 * np) << 16;   // LBO of the B tile: rows per chunk x 16 bytes
+#pragma unroll 1
+                for (int t = 0; t < kTiles; ++t) {
+                    if (s > 0) {
+                        const uint32_t pp = (k - 1) & 1;
+                        if (t == 0) mbar_wait(bars + 8 * (kBarActReady + 0), pp, err, 3);
+                        if (t + 1 < kTiles) mbar_wait(bars + 8 * (kBarActReady + t + 1), pp, err, 4);
+                    }
+                    fence_after();
+                    if (elect_one()) {
+                        const uint32_t d = tm + (uint32_t)(t * kAccCols);
+                        const uint32_t a0 = act16 + kLead + 128 * t;
+#pragma unroll 2
+                        for (int u = 0; u < nu; ++u) {
+                            const int2 e = ut[u];
+                            const uint32_t a_lo32 = ((a0 + (uint32_t)e.x) & 0x3FFFu) | ((uint32_t)e.y << 16);
+                            const uint32_t b_lo32 = ((w16 + (uint32_t)(u * tile16)) & 0x3FFFu) | b_lbo;
+                            const uint64_t da_hi = make_desc(a_lo32), da_lo = make_desc(a_lo32 + kLo16);
+                            const uint64_t db = make_desc(b_lo32);
+                            if (!fin) {
+                                umma_f16(d, da_hi, db, id_a, u > 0);      // hi x [Whi | Wlo] -> columns [0, 2 NP)
+                                umma_f16(d, da_lo, db, id_b, 1);          // lo x Whi        -> columns [0, NP)
+                            } else {
+                                umma_f16(d, da_hi, db, id_a, u > 0);      // hi x Whi (48 taps)
+                                umma_f16(d, da_lo, db, id_a, 1);          // lo x Whi
+                                umma_f16(d, da_hi, make_desc(b_lo32 + (uint32_t)np), id_a, 1);   // hi x Wlo (rows 48..95)
+                            }
+                        }
+                        umma_commit(bars + 8 * (kBarAccFull + t));
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) umma_commit(bars + 8 * (kBarWFree + wb));
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ================= weight producer =================
+        uint32_t it = 0;
+        for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
+#pragma unroll 1
+            for (int s = 0; s < NS; ++s) {
+                const uint32_t k = it * NS + s;
+                const int wb = k & 1;
+                if (k >= 2) mbar_wait(bars + 8 * (kBarWFree + wb), ((k >> 1) - 1) & 1, err, 5);
+                if (lane == 0) {
+                    const uint32_t bytes = (uint32_t)step_w_bytes(ARCH, s);
+                    const uint32_t full = bars + 8 * (kBarWFull + wb);
+                    mbar_expect_tx(full, bytes);
+                    const unsigned char* src = p.wimg + step_w_off(ARCH, s);
+                    const uint32_t dst = smem_u32(smem + smem_w_off(ARCH, wb));
+                    for (uint32_t o = 0; o < bytes; o += 16384u) bulk_g2s(dst + o, src + o, bytes - o < 16384u ? bytes - o : 16384u, full);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= kCtrlWarps) {
+        // ================= epilogue groups =================
+        Ctx c;
+        c.smem = smem;
+        c.act = act;
+        c.bars = bars;
+        c.tm = tm;
+        c.bias = s_bias;
+        c.bnd = bnd;
+        c.err = err;
+        c.lane = lane;
+        c.quad = warp & 3;
+        c.grp = (warp - kCtrlWarps) >> 2;
+        c.et = (warp - kCtrlWarps) * 32 + lane;
+        c.skip = p.skip + (size_t)blockIdx.x * skip_floats_per_cta(ARCH);
+        c.priv = reinterpret_cast<float*>(act + 2 * kPlane16 * 16) + (warp - kCtrlWarps) * kRows;
+        float amax = 0.f;
+        const float bias_f = s_bias[(NL - 1) * 32];
+        uint32_t it = 0;
+        for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
+            const long long g0 = batch * kFB;
+            const long long left = p.total_rows - g0;
+            c.nf = left < kFB ? (int)left : kFB;
+            c.g0 = g0;
+            if (c.et < kFB) {
+                long long lo = 0, hi = 0;
+                if (c.et < c.nf) locate(p.row_off, p.n_utt, g0 + c.et, lo, hi);
+                bnd[2 * c.et] = lo;
+                bnd[2 * c.et + 1] = hi;
+            }
+            epi_bar();   // bounds visible; every MMA of the previous batch has completed (its epilogues waited)
+            // the output layer's accumulators of the previous batch overlaid planes 2 and 3 (hi),
+            // halo rows included: those must read as zero again before any tap touches them
+            if (it > 0 && c.et < 2 * 16) {
+                const int pl = 2 + (c.et >> 4), hr = c.et & 15;
+                const int row = hr < 8 ? hr : kLead + kRows + (hr - 8);
+                reinterpret_cast<uint4*>(act)[pl * kPlane16 + row] = make_uint4(0, 0, 0, 0);
+            }
+            // ---- stage the first layer's input: "channel" = time tap, rows g-3 .. g+4 of the utterance
+#pragma unroll 1
+            for (int r = c.et; r < kRows; r += 32 * kEpiWarps) {
+                const int fi = r / kFS, b = r - fi * kFS;
+                float v[8];
+                if (fi < c.nf && b < kBins) {
+                    const long long lo = bnd[2 * fi], hi = bnd[2 * fi + 1];
+                    const long long g = g0 + fi;
+#pragma unroll
+                    for (int tt = 0; tt < 8; ++tt) {
+                        const long long src = g + tt - 3;
+                        v[tt] = (src >= lo && src < hi) ? __ldg(p.in + src * kBins + b) : 0.f;
+                        amax = fmaxf(amax, fabsf(v[tt]));
+                    }
+                } else {
+#pragma unroll
+                    for (int tt = 0; tt < 8; ++tt) v[tt] = 0.f;
+                }
+                store_split8(act, 0, kLead + r, v);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * kBarInReady);
+
+            epi_steps<ARCH, 0>(c, it * NS, amax);
+
+            epi_bar();   // every warp's partial sums of the output layer are complete
+            {
+                const float* pw = reinterpret_cast<const float*>(act + 2 * kPlane16 * 16);
+                for (int i = c.et; i < c.nf * kBins; i += 32 * kEpiWarps) {
+                    const int fi = i / kBins, b = i - fi * kBins;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kEpiWarps; ++w) acc += pw[w * kRows + fi * kFS + b];
+                    p.out[(g0 + fi) * kBins + b] = acc + bias_f;
+                }
+            }
+        }
+        // range guard: non-negative floats order like their bit patterns
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+        if (lane == 0) atomicMax(p.flags, __float_as_uint(amax));
+    }
+
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: weight image, launch
+// ------------------------------------------------------------------------------------------
+static inline void split_half(float w, uint16_t& hi, uint16_t& lo) {
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    memcpy(&hi, &h, 2);
+    memcpy(&lo, &l, 2);
+}
+
+}  // namespace tc
+
+int tc_image_bytes(int arch) { return tc::w_image_bytes(arch); }
+int tc_bias_floats(int arch) { return tc::n_steps(arch) * 32; }
+size_t tc_skip_floats_per_cta(int arch) { return tc::skip_floats_per_cta(arch); }
+int tc_smem_bytes(int arch) { return tc::smem_total(arch); }
+
+// folded: canonical BN-folded weights (rced_folded_weight_count); img: tc_image_bytes; bias: tc_bias_floats
+void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* bias) {
+    using namespace tc;
+    const int nl = num_layers(arch), ns = n_steps(arch);
+    memset(img, 0, (size_t)w_image_bytes(arch));
+    for (int i = 0; i < ns * 32; ++i) bias[i] = 0.f;
+    uint16_t* im = reinterpret_cast<uint16_t*>(img);
+    for (int s = 0; s < ns; ++s) {
+        const int li = step_layer(arch, s);
+        const LSpec sp = spec(arch, li);
+        const float* k = folded + folded_off(arch, li);   // [kh][kw][cin][cout]
+        const float* b = k + (size_t)sp.kh * sp.kw * sp.cin * sp.cout;
+        const int rows = step_tile_rows(arch, s), np = step_np(arch, s), nc = step_chunks(arch, s);
+        uint16_t* base = im + step_w_off(arch, s) / 2;
+        for (int u = 0; u < step_units(arch, s); ++u)
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ch = 2 * u + cc;
+                if (ch >= nc) continue;
+                for (int n = 0; n < rows; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        float w = 0.f;
+                        const bool want_lo = n >= np;
+                        const int nn = want_lo ? n - np : n;
+                        if (is_final(arch, s)) {
+                            const int tap = (s - (nl - 1)) * kFinalTaps + nn, ci = 8 * ch + e;
+                            if (tap < sp.kw && ci < sp.cin) w = k[((size_t)tap * sp.cin + ci) * sp.cout];
+                        } else {
+                            const int g = ch / sp.kw, j = ch % sp.kw, ci = 8 * g + e;
+                            if (nn < sp.cout && ci < cin_eff(arch, s)) {
+                                // first layer: "channel" ci is the time tap (kh index), cin == 1
+                                w = s == 0 ? k[(((size_t)ci * sp.kw + j) * sp.cin + 0) * sp.cout + nn]
+                                           : k[(((size_t)0 * sp.kw + j) * sp.cin + ci) * sp.cout + nn];
+                            }
+                        }
+                        uint16_t hi, lo;
+                        split_half(w, hi, lo);
+                        base[((size_t)u * 2 * rows + (size_t)cc * rows + n) * 8 + e] = want_lo ? lo : hi;
+                    }
+            }
+        if (is_final(arch, s)) bias[s * 32] = b[0];
+        else
+            for (int o = 0; o < sp.cout; ++o) bias[s * 32 + o] = b[o];
+    }
+    // the epilogue role reads the final bias from row NL-1 (the first final pass)
+}
+
+template <int ARCH>
+static cudaError_t launch_tc_t(const tc::TcParams& p, int num_sms, cudaStream_t stream) {
+    constexpr int smem = tc::smem_total(ARCH);
+    static_assert(smem <= 227 * 1024, "activation planes + weight double buffer must fit one SM's shared memory");
+    cudaError_t e = cudaFuncSetAttribute(tc::rced_net_tc_kernel<ARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    long long ctas = (p.total_rows + tc::kFB - 1) / tc::kFB;
+    if (ctas > num_sms) ctas = num_sms;
+    if (ctas < 1) return cudaSuccess;
+    tc::rced_net_tc_kernel<ARCH><<<(unsigned)ctas, tc::kThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_net_tc(int arch, const NetParams& np, const unsigned char* wimg, const float* bias, float* skip,
+                          unsigned int* flags, int num_sms, cudaStream_t stream) {
+    tc::TcParams p;
+    p.wimg = wimg;
+    p.bias = bias;
+    p.in = np.in;
+    p.out = np.out;
+    p.row_off = np.row_off;
+    p.n_utt = np.n_utt;
+    p.total_rows = np.total_rows;
+    p.skip = skip;
+    p.flags = flags;
+    switch (arch) {
+        case 1: return launch_tc_t<1>(p, num_sms, stream);
+        case 2: return launch_tc_t<2>(p, num_sms, stream);
+        case 3: return launch_tc_t<3>(p, num_sms, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace rced

@@ -1,0 +1,118 @@
+// Layout of the tensor-core variant of the fused network kernel (rced_net_tc.cu), shared by
+// the kernel, the host-side weight packer and the tests.
+//
+// The conv layers of model_utils/model.py run as implicit GEMMs on tcgen05 WITHOUT an im2col
+// copy: activations live in shared memory as FP16 "chunk planes" A[cg][row][8 channels]
+// (16 bytes per row and channel group), rows = (frame, bin) flattened with a frame stride of
+// 136 (129 bins + 7 zero rows, the SAME-padding halo of both neighbours), and every filter tap
+// is one K-major, no-swizzle matrix descriptor whose start address is the plane shifted by
+// (tap - pad) rows (tools/umma_probe.cu proves the addressing).  FP32 accuracy comes from an
+// error-compensated split x = hi + lo (two FP16 numbers, 22 significant bits):
+//   x*w ~= hi*Whi + hi*Wlo + lo*Whi     (FP32 accumulation in tensor memory)
+// issued as two instructions per K step: A_hi x [Whi | Wlo] (N = 2*NP) and A_lo x Whi (N = NP).
+#pragma once
+#include "rced_arch.cuh"
+
+namespace rced {
+namespace tc {
+
+constexpr int kFB = 7;                        // frames per CTA batch
+constexpr int kFS = 136;                      // rows per frame in the flattened row space
+constexpr int kLead = 8;                      // zero rows in front of the first frame
+constexpr int kTiles = 8;                     // M = 128 row tiles per batch
+constexpr int kRows = kTiles * 128;           // rows covered by the tiles (7 * 136 = 952 used)
+constexpr int kRowsAlloc = kLead + kRows + 8; // + zero rows behind the last tile
+constexpr int kPlane16 = kRowsAlloc;          // plane stride in 16-byte units
+constexpr int kPlanes = 4;                    // channel groups of 8 (<= 32 channels)
+constexpr int kLo16 = kPlanes * kPlane16;     // offset of the lo planes behind the hi planes
+constexpr int kActBytes = 2 * kPlanes * kPlane16 * 16;
+constexpr int kAccCols = 64;                  // tensor-memory columns per tile
+constexpr int kFinalTaps = 48;                // taps of the (1,129) layer per pass (N of the pass)
+constexpr int kFinalPasses = 3;
+constexpr int kCtrlWarps = 4;                 // warp 0: MMA issue, warp 1: weight producer, 2-3: idle
+constexpr int kEpiWarps = 8;                  // two groups of four (one per tensor-memory lane quadrant)
+constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
+constexpr int kOutStride = 132;               // floats per frame of the output accumulator
+
+static_assert(kFB * kFS <= kRows, "frames of a batch must fit the row tiles");
+static_assert(kFS - kBins >= 6 && kLead >= 6, "zero rows must cover the widest SAME pad (kw = 13)");
+
+// steps: conv layers 0 .. NL-2, then kFinalPasses passes of the (1,129) layer
+RCED_HD constexpr int n_steps(int arch) { return num_layers(arch) - 1 + kFinalPasses; }
+RCED_HD constexpr bool is_final(int arch, int s) { return s >= num_layers(arch) - 1; }
+RCED_HD constexpr int step_layer(int arch, int s) { return is_final(arch, s) ? num_layers(arch) - 1 : s; }
+RCED_HD constexpr int step_np(int arch, int s) {
+    return is_final(arch, s) ? kFinalTaps : (spec(arch, s).cout <= 16 ? 16 : 32);
+}
+RCED_HD constexpr int step_groups(int arch, int s) {
+    return is_final(arch, s) ? (spec(arch, num_layers(arch) - 1).cin + 7) / 8 : (cin_eff(arch, s) + 7) / 8;
+}
+RCED_HD constexpr int step_chunks(int arch, int s) {
+    return is_final(arch, s) ? step_groups(arch, s) : spec(arch, s).kw * step_groups(arch, s);
+}
+RCED_HD constexpr int step_units(int arch, int s) { return (step_chunks(arch, s) + 1) / 2; }
+// B tile of one unit: [2 chunks][rows][8 halfs]; rows = 2*NP (Whi | Wlo), final pass 96 (48 | 48)
+RCED_HD constexpr int step_tile_rows(int arch, int s) { return 2 * step_np(arch, s); }
+RCED_HD constexpr int step_tile_bytes(int arch, int s) { return 2 * step_tile_rows(arch, s) * 16; }
+RCED_HD constexpr int step_w_bytes(int arch, int s) { return step_units(arch, s) * step_tile_bytes(arch, s); }
+RCED_HD constexpr int step_w_off(int arch, int s) {
+    int o = 0;
+    for (int i = 0; i < s; ++i) o += step_w_bytes(arch, i);
+    return o;
+}
+RCED_HD constexpr int w_image_bytes(int arch) { return step_w_off(arch, n_steps(arch)); }
+RCED_HD constexpr int max_step_w_bytes(int arch) {
+    int m = 0;
+    for (int i = 0; i < n_steps(arch); ++i)
+        if (step_w_bytes(arch, i) > m) m = step_w_bytes(arch, i);
+    return m;
+}
+RCED_HD constexpr int unit_base(int arch, int s) {
+    int o = 0;
+    for (int i = 0; i < s; ++i) o += step_units(arch, i);
+    return o;
+}
+RCED_HD constexpr int total_units(int arch) { return unit_base(arch, n_steps(arch)); }
+
+// A-operand addressing of chunk c of step s, in 16-byte units relative to row (kLead + 128 t)
+// of plane 0: channel group g = c / kw lives in plane g, tap j = c % kw reads rows shifted by j - pad
+RCED_HD constexpr int chunk_off16(int arch, int s, int c) {
+    if (is_final(arch, s)) return c * kPlane16;
+    const int kw = spec(arch, s).kw;
+    return (c / kw) * kPlane16 + (c % kw) - (kw - 1) / 2;
+}
+
+// ---- skip tensors: FP32 in a per-CTA global scratch, [group of 8 channels][row][8] ----------
+RCED_HD constexpr int skip_c8(int arch, int slot) {
+    for (int i = 0; i < num_layers(arch); ++i)
+        if (spec(arch, i).save == slot) return (spec(arch, i).cout + 7) / 8;
+    return 0;
+}
+RCED_HD constexpr int skip_c8_base(int arch, int slot) {
+    int o = 0;
+    for (int s = 0; s < slot; ++s) o += skip_c8(arch, s);
+    return o;
+}
+RCED_HD constexpr int skip_c8_total(int arch) { return skip_c8_base(arch, 8); }
+RCED_HD constexpr size_t skip_floats_per_cta(int arch) { return (size_t)skip_c8_total(arch) * kRows * 8; }
+
+// ---- shared memory carve-up (bytes) ---------------------------------------------------------
+RCED_HD constexpr int pad128(int x) { return (x + 127) & ~127; }
+RCED_HD constexpr int smem_w_off(int arch, int buf) { return kActBytes + buf * pad128(max_step_w_bytes(arch)); }
+RCED_HD constexpr int smem_tab_off(int arch) { return smem_w_off(arch, 2); }                        // int2[total_units]
+RCED_HD constexpr int smem_step_off(int arch) { return smem_tab_off(arch) + pad128(8 * total_units(arch)); }   // int4[n_steps]
+RCED_HD constexpr int smem_bias_off(int arch) { return smem_step_off(arch) + pad128(16 * n_steps(arch)); }     // float[n_steps][32]
+RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 128 * n_steps(arch); }             // float[kFB][kOutStride]
+RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + pad128(4 * kFB * kOutStride); }     // long long[kFB][2]
+RCED_HD constexpr int smem_bar_off(int arch) { return smem_bnd_off(arch) + 128; }                              // mbarriers
+RCED_HD constexpr int smem_total(int arch) { return smem_bar_off(arch) + 256; }
+
+// mbarrier slots (8 bytes each) inside the barrier block
+constexpr int kBarAccFull = 0;     // [kTiles]  tcgen05.commit after the last MMA of (step, tile)
+constexpr int kBarActReady = 8;    // [kTiles]  epilogue of (step, tile) done (planes written, accumulator free)
+constexpr int kBarWFull = 16;      // [2]       weights of a step landed in buffer b
+constexpr int kBarWFree = 18;      // [2]       MMAs reading buffer b complete
+constexpr int kBarInReady = 20;    //           layer-0 input of the batch staged
+
+}  // namespace tc
+}  // namespace rced

@@ -94,6 +94,18 @@ class Enhancer(object):
     def set_skip_in_tmem(self, enable):
         _lib.check(self.lib.rced_set_skip_in_tmem(self._h, 1 if enable else 0))
 
+    def set_variant(self, variant):
+        """"ffma" (FP32 FFMA kernel, default) or "tc" (tcgen05 tensor-core kernel, FP16 x3 split with the
+        FFMA kernel as stream-ordered fall-back when an activation leaves the FP16 range)."""
+        v = {"ffma": _lib.VARIANT_FFMA, "tc": _lib.VARIANT_TC}.get(variant, variant)
+        _lib.check(self.lib.rced_set_variant(self._h, int(v)))
+
+    def tc_status(self):
+        """(largest |activation| stored as FP16, protocol error code) of the last tensor-core launch."""
+        m, e = ctypes.c_float(), ctypes.c_uint()
+        _lib.check(self.lib.rced_tc_status(self._h, ctypes.byref(m), ctypes.byref(e)))
+        return float(m.value), int(e.value)
+
     # ------------------------------------------------------------------ device-level ops
     def _stream_ptr(self, stream):
         if stream is None:

@@ -38,6 +38,9 @@ extern "C" {
 #define RCED_ARCH_V2 2       /* FullyCNNSEModelV2 (model_utils/model.py:32-61) */
 #define RCED_ARCH_V3 3       /* FullyCNNSEModelV3 (model_utils/model.py:64-96) */
 
+#define RCED_VARIANT_FFMA 0  /* FP32 FFMA network kernel (rced_net.cu), the default          */
+#define RCED_VARIANT_TC   1  /* tcgen05 tensor-core kernel, FP16 x3 error-compensated split  */
+
 #define RCED_OK 0
 #define RCED_ERR_ARG   (-1)
 #define RCED_ERR_CUDA  (-2)
@@ -97,6 +100,35 @@ int rced_device(const rced_handle* h);
  * 0: they go to a per-warp scratch area in global memory (L2 resident).  Both are
  * exercised by the parity tests. */
 int rced_set_skip_in_tmem(rced_handle* h, int enable);
+
+/* Network kernel behind rced_forward / rced_enhance (same call sites as K2 below:
+ * model_utils/tester.py:85-90, infer.py:62-65).
+ *   RCED_VARIANT_FFMA (default): register-tiled FP32 FFMA kernel.
+ *   RCED_VARIANT_TC: implicit-GEMM kernel on the 5th-generation tensor cores.  Activations and
+ *     weights are split into FP16 hi + lo pairs (22 significant bits) and multiplied as
+ *     hi*Whi + hi*Wlo + lo*Whi with FP32 accumulation; max relative error vs the float64 oracle
+ *     is stated in tests/test_gpu_parity.py.  FP16 overflows beyond 65504: the kernel records the
+ *     largest |activation| it stored and, stream-ordered, the FFMA kernel recomputes the call
+ *     when that range was exceeded.  Refused (RCED_ERR_STATE) if a folded weight exceeds 65504. */
+int rced_set_variant(rced_handle* h, int variant);
+int rced_variant(const rced_handle* h);
+/* Largest |activation| and protocol-error code of the last tensor-core launch (synchronises the
+ * device; diagnostics and tests only). */
+int rced_tc_status(rced_handle* h, float* max_abs, unsigned int* protocol_error);
+
+/* Host-side packing of the tensor-core kernel's weight image (FP16 hi/lo B-operand tiles per
+ * layer, tap and 8-channel group) and FP32 bias table; exported so that tests can check the layout
+ * and arithmetic without a GPU.  rced_tc_layout writes: out[0]=steps, [1]=units, [2]=image bytes,
+ * [3]=shared-memory bytes, [4]=plane stride (16-byte units), [5]=lead rows, [6]=rows per frame,
+ * [7]=frames per batch, [8]=row tiles, [9]=offset of the lo planes (16-byte units), [10]=taps per
+ * pass of the output layer, [11]=skip scratch floats per CTA; then per step 6 values (units,
+ * first unit, NP, tile bytes, image offset, is_final) and per unit 2 values (start offset and LBO
+ * of the A descriptor in 16-byte units).  n >= 12 + 6*steps + 2*units. */
+int64_t rced_tc_image_bytes(int arch);
+int64_t rced_tc_bias_count(int arch);
+int rced_tc_pack_weights(int arch, const float* folded, size_t n_folded, void* image, size_t image_bytes,
+                         float* bias, size_t n_bias);
+int rced_tc_layout(int arch, int64_t* out, int n);
 
 /* ---- the three kernels of the path ----------------------------------------------- */
 

@@ -1,0 +1,60 @@
+"""CPU: layout and arithmetic of the tensor-core network kernel, without a GPU.
+
+tools/tc_emulator.py executes the kernel's data flow (FP16 hi/lo weight image and descriptor table
+from librced_b200.so, flattened row space, two instructions per K step, "taps in N" output layer)
+in numpy.  Comparing it with the float64 oracle pins (a) the weight image / descriptor arithmetic
+the CUDA kernel shares through csrc/rced_tc.cuh and (b) the accuracy of the FP16 x3 split, which
+the north star requires to be stated separately from the FP32 path: max |err| / max |ref| <= 1e-4."""
+import numpy as np
+import pytest
+
+from fullycnnspeechenhancement_b200 import _lib
+from fullycnnspeechenhancement_b200.model_utils import fold
+from oracle import network
+
+TC_TOL = 1e-4   # same bar as the FP32 kernel (BASELINE.json north_star); measured ~1e-6
+
+
+def oracle_ragged(name, w, mag, row_off):
+    out = np.zeros_like(mag, dtype=np.float64)
+    for u in range(len(row_off) - 1):
+        a, b = row_off[u], row_off[u + 1]
+        out[a:b] = network.forward(name, w, mag[a:b][None, :, :, None], np.float64)[0, :, :, 0]
+    return out
+
+
+@pytest.mark.parametrize("name", ["FullyCNN", "FullyCNNV2", "FullyCNNV3"])
+def test_tc_emulator_matches_oracle(name):
+    import tc_emulator
+    lib = _lib.lib()
+    w = network.random_weights(name, 11, True)
+    folded = fold.fold_batch_norm(w, name)
+    rng = np.random.default_rng(5)
+    # ragged batch: utterance boundaries inside a 7-frame batch, a 1-frame utterance, a partial last batch
+    lens = [5, 1, 9, 3]
+    row_off = np.concatenate([[0], np.cumsum(lens)])
+    mag = np.abs(rng.normal(0, 3, (row_off[-1], 129))).astype(np.float32)
+    ref = oracle_ragged(name, w, mag, row_off)
+    got, amax = tc_emulator.run(lib, fold.arch_id(name), folded, mag, row_off, network.layer_table(name))
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < TC_TOL, err
+    assert err < 2e-5, "FP16 x3 split should be within a few 1e-6 of float64: %g" % err
+    assert 0 < amax < 65504
+
+
+def test_tc_layout_fits_the_sm():
+    import tc_emulator
+    lib = _lib.lib()
+    for arch in (1, 2, 3):
+        lay = tc_emulator.layout(lib, arch)
+        assert lay["smem"] <= 227 * 1024
+        assert lay["tiles"] * 64 <= 512                      # tensor-memory columns
+        assert lay["fb"] * lay["fs"] <= lay["tiles"] * 128   # frames of a batch fit the row tiles
+        # every A descriptor stays inside the allocated planes, LBO is positive
+        for st in lay["steps"]:
+            for u in range(st["units"]):
+                off, lbo = lay["units"][st["unit_base"] + u]
+                assert lbo > 0
+                assert lay["lead"] + off >= 0
+                assert lay["lead"] + 128 * (lay["tiles"] - 1) + off + lbo + 128 <= 4 * lay["plane16"]
+            assert st["tile_bytes"] % 16 == 0 and st["w_off"] % 16 == 0

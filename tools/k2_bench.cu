@@ -38,7 +38,7 @@ int main(int argc, char** argv) {
     cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dro, ro.data(), ro.size() * 8, cudaMemcpyHostToDevice);
     NetParams p;
-    p.packed = dw; p.in = dx; p.out = dy; p.row_off = dro; p.n_utt = n_utt; p.total_rows = rows; p.skip_scratch = nullptr;
+    p.packed = dw; p.in = dx; p.out = dy; p.row_off = dro; p.n_utt = n_utt; p.total_rows = rows; p.skip_scratch = nullptr; p.guard = nullptr;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);

@@ -1,0 +1,153 @@
+"""numpy emulator of the tensor-core network kernel's data flow (development / test aid).
+
+It executes exactly the address arithmetic of csrc/rced_net_tc.cu on the CPU: the FP16 hi/lo
+weight image and bias table produced by rced_tc_pack_weights, the per-unit A-descriptor table of
+rced_tc_layout (start offset and leading-dimension offset in 16-byte units, rows linear at 16
+bytes), the flattened (frame, bin) row space with its zero halo rows, in-place plane updates,
+the two instructions per K step (A_hi x [Whi | Wlo], A_lo x Whi) with FP32 accumulation, the
+"taps in N" passes of the (1,129) layer with the same-frame mask, and the FP32 skip scratch.
+It needs no GPU, only the host functions of librced_b200.so; tests/test_tc_cpu.py compares it
+with the float64 oracle, which pins both the layout and the accuracy of the FP16 x3 split.
+"""
+import ctypes
+
+import numpy as np
+
+BINS = 129
+
+
+def layout(lib, arch):
+    out = (ctypes.c_int64 * 4096)()
+    assert lib.rced_tc_layout(arch, out, len(out)) == 0, lib.rced_last_error()
+    ns, nu = out[0], out[1]
+    lay = dict(ns=ns, nu=nu, image_bytes=out[2], smem=out[3], plane16=out[4], lead=out[5], fs=out[6], fb=out[7],
+               tiles=out[8], lo16=out[9], final_taps=out[10], skip_floats=out[11], steps=[], units=[])
+    for s in range(ns):
+        o = out[12 + 6 * s: 18 + 6 * s]
+        lay["steps"].append(dict(units=o[0], unit_base=o[1], np=o[2], tile_bytes=o[3], w_off=o[4], final=bool(o[5])))
+    u0 = 12 + 6 * ns
+    lay["units"] = [(out[u0 + 2 * i], out[u0 + 2 * i + 1]) for i in range(nu)]
+    return lay
+
+
+def pack(lib, arch, folded):
+    folded = np.ascontiguousarray(folded, np.float32)
+    img = np.zeros(lib.rced_tc_image_bytes(arch), np.uint8)
+    bias = np.zeros(lib.rced_tc_bias_count(arch), np.float32)
+    rc = lib.rced_tc_pack_weights(arch, folded.ctypes.data_as(ctypes.c_void_p), folded.size,
+                                  img.ctypes.data_as(ctypes.c_void_p), img.size,
+                                  bias.ctypes.data_as(ctypes.c_void_p), bias.size)
+    assert rc == 0, lib.rced_last_error()
+    return img, bias
+
+
+def split(v):
+    v = np.asarray(v, np.float32)
+    hi = v.astype(np.float16)
+    lo = (v - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def run(lib, arch, folded, mag, row_off, table):
+    """mag [rows,129] float32 (packed ragged batch), row_off [n_utt+1] -> pred [rows,129] float32.
+    ``table``: the model's layer table (scope / skip / act / skip_after_act per layer) -- the emulator
+    takes the graph wiring from the caller so that it does not share the C++ table for it."""
+    lay = layout(lib, arch)
+    img, bias = pack(lib, arch, folded)
+    halfs = img.view(np.float16)
+    P16, LEAD, FS, FB, TILES, LO16 = lay["plane16"], lay["lead"], lay["fs"], lay["fb"], lay["tiles"], lay["lo16"]
+    ROWS = TILES * 128
+    mag = np.asarray(mag, np.float32)
+    row_off = np.asarray(row_off, np.int64)
+    total = mag.shape[0]
+    pred = np.zeros((total, BINS), np.float32)
+    nl = len(table)
+    scopes = [L["scope"] for L in table]
+    amax = 0.0
+
+    r_idx = np.arange(ROWS)
+    fi_of, b_of = r_idx // FS, r_idx % FS
+
+    for g0 in range(0, total, FB):
+        nf = min(FB, total - g0)
+        valid = (fi_of < nf) & (b_of < BINS)
+        # flat[16-byte unit][8 halfs]: hi planes then lo planes, like the shared-memory array
+        flat = np.zeros((2 * LO16, 8), np.float16)
+        # ---- staging of the first layer's input ("channel" = time tap)
+        v = np.zeros((ROWS, 8), np.float32)
+        for fi in range(nf):
+            g = g0 + fi
+            u = int(np.searchsorted(row_off, g, side="right") - 1)
+            lo_, hi_ = row_off[u], row_off[u + 1]
+            for tt in range(8):
+                src = g + tt - 3
+                if lo_ <= src < hi_:
+                    v[fi * FS: fi * FS + BINS, tt] = mag[src]
+        amax = max(amax, float(np.abs(v).max()))
+        h, l = split(v)
+        flat[LEAD: LEAD + ROWS] = h
+        flat[LO16 + LEAD: LO16 + LEAD + ROWS] = l
+        saved = {}
+        outrow = np.zeros(ROWS, np.float32)
+        for s, st in enumerate(lay["steps"]):
+            NP = st["np"]
+            rows_b = 2 * NP
+            tile_h = st["tile_bytes"] // 2
+            D = np.zeros((ROWS, 64), np.float32)
+            for t in range(TILES):
+                for u in range(st["units"]):
+                    off16, lbo16 = lay["units"][st["unit_base"] + u]
+                    start = LEAD + 128 * t + off16
+                    a_hi = np.concatenate([flat[start: start + 128], flat[start + lbo16: start + lbo16 + 128]], axis=1)
+                    a_lo = np.concatenate([flat[LO16 + start: LO16 + start + 128],
+                                           flat[LO16 + start + lbo16: LO16 + start + lbo16 + 128]], axis=1)
+                    tile = halfs[st["w_off"] // 2 + u * tile_h: st["w_off"] // 2 + (u + 1) * tile_h].reshape(2, rows_b, 8)
+                    B = np.concatenate([tile[0], tile[1]], axis=1).astype(np.float32)   # [rows_b][16]
+                    a_hi = a_hi.astype(np.float32)
+                    a_lo = a_lo.astype(np.float32)
+                    sl = slice(128 * t, 128 * t + 128)
+                    if not st["final"]:
+                        pa = a_hi @ B.T
+                        if u == 0:
+                            D[sl, :rows_b] = pa
+                        else:
+                            D[sl, :rows_b] += pa
+                        D[sl, :NP] += a_lo @ B[:NP].T
+                    else:
+                        pa = a_hi @ B[:NP].T
+                        if u == 0:
+                            D[sl, :NP] = pa
+                        else:
+                            D[sl, :NP] += pa
+                        D[sl, :NP] += a_lo @ B[:NP].T
+                        D[sl, :NP] += a_hi @ B[NP:].T
+            if not st["final"]:
+                L = table[s]
+                cout = L["cout"]
+                cg = (cout + 7) // 8
+                x = D[:, :cg * 8] + D[:, NP:NP + cg * 8] + bias[s * 32: s * 32 + cg * 8]
+                if L["skip"] is not None and not L["skip_after_act"]:
+                    x = x + saved[L["skip"]]
+                if L["act"]:
+                    x = np.maximum(x, 0)
+                if L["skip"] is not None and L["skip_after_act"]:
+                    x = x + saved[L["skip"]]
+                x = np.where(valid[:, None], x, 0).astype(np.float32)
+                amax = max(amax, float(np.abs(x).max()))
+                saved[scopes[s]] = x
+                h, l = split(x)
+                for g in range(cg):
+                    flat[g * P16 + LEAD: g * P16 + LEAD + ROWS] = h[:, 8 * g: 8 * g + 8]
+                    flat[LO16 + g * P16 + LEAD: LO16 + g * P16 + LEAD + ROWS] = l[:, 8 * g: 8 * g + 8]
+            else:
+                p = s - (nl - 1)
+                for i in range(lay["final_taps"]):
+                    tap = p * lay["final_taps"] + i
+                    ob = b_of - tap + 64
+                    m = valid & (ob >= 0) & (ob < BINS)
+                    ro = r_idx - tap + 64
+                    np.add.at(outrow, ro[m], D[m, i])
+        bias_f = bias[(nl - 1) * 32]
+        for fi in range(nf):
+            pred[g0 + fi] = outrow[fi * FS: fi * FS + BINS] + bias_f
+    return pred, amax
