@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -483,8 +484,23 @@ int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n
         // tensor-core kernel reported a protocol error -- stream-ordered, no host synchronisation
         if ((e = cudaMemsetAsync(h->d_tc_flags, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream)) != cudaSuccess)
             return cuda_fail(e, "cudaMemsetAsync(tc flags)");
-        e = launch_net_tc(h->arch, p, h->d_tc_img, h->d_tc_bias, h->d_tc_skip, h->d_tc_flags, h->num_sms, (cudaStream_t)stream);
+        // development aid: RCED_TC_TRACE=<file> dumps clock64 stamps of CTA 0's second batch (synchronises)
+        const char* trace_path = getenv("RCED_TC_TRACE");
+        long long* d_trace = nullptr;
+        const int slots = tc_trace_slots(h->arch);
+        if (trace_path && cudaMalloc(&d_trace, slots * sizeof(long long)) == cudaSuccess) cudaMemset(d_trace, 0, slots * sizeof(long long));
+        e = launch_net_tc(h->arch, p, h->d_tc_img, h->d_tc_bias, h->d_tc_skip, h->d_tc_flags, d_trace, h->num_sms, (cudaStream_t)stream);
         count_launch();
+        if (d_trace) {
+            std::vector<long long> t(slots);
+            if (cudaMemcpy(t.data(), d_trace, slots * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+                if (FILE* f = fopen(trace_path, "w")) {
+                    for (int i = 0; i < slots; ++i) fprintf(f, "%lld%c", t[i], (i + 1) % tc::kTraceEvents == 0 ? '\n' : ' ');
+                    fclose(f);
+                }
+            }
+            cudaFree(d_trace);
+        }
         if (e != cudaSuccess) return cuda_fail(e, "rced_forward launch (tensor-core variant)");
         p.guard = h->d_tc_flags;
     }

@@ -52,8 +52,9 @@ int tc_bias_floats(int arch);
 size_t tc_skip_floats_per_cta(int arch);
 int tc_smem_bytes(int arch);
 void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* bias);
+int tc_trace_slots(int arch);
 cudaError_t launch_net_tc(int arch, const NetParams& p, const unsigned char* wimg, const float* bias, float* skip,
-                          unsigned int* flags, int num_sms, cudaStream_t stream);
+                          unsigned int* flags, long long* trace, int num_sms, cudaStream_t stream);
 cudaError_t launch_stft(const StftParams& p, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, long long max_rows_per_utt, cudaStream_t stream);
 cudaError_t upload_tables_stft();    // twiddles + window tables of K1 -> current device

@@ -54,7 +54,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Bounded wait: a protocol error must end the kernel with an error flag, not hang the GPU.  Once
 // any wait has timed out every other wait of the grid gives up at its next check of the flag.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err, int code) {
+    // fast path: the non-blocking test costs a fraction of try_wait (tools/umma_probe lat: 168 cycles
+    // for a try_wait on a phase that is already complete)
+    if (mbar_test(bar, parity)) return;
     for (int it = 0; it < (1 << 21); ++it) {
         uint32_t ok;
         asm volatile(
@@ -68,6 +82,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
         if ((it & 255) == 255 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) return;
     }
     atomicMax(err, (unsigned int)code);
+}
+__device__ __forceinline__ void st_release(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -120,16 +142,30 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void store_split8(unsigned char* act, int cg, int q, const float (&v)[8]) {
+// rows that are not (frame, bin) rows of the batch -- the halo rows between frames and everything
+// behind the last frame -- are stored as zeros whatever was computed for them
+__device__ __forceinline__ void store_split8(unsigned char* act, int cg, int q, const float (&v)[8], bool valid) {
     uint4 h, l;
     split2(v[0], v[1], h.x, l.x);
     split2(v[2], v[3], h.y, l.y);
     split2(v[4], v[5], h.z, l.z);
     split2(v[6], v[7], h.w, l.w);
     uint4* ph = reinterpret_cast<uint4*>(act) + cg * kPlane16 + q;
-    ph[0] = h;
-    ph[kLo16] = l;
+    if (valid) {
+        ph[0] = h;
+        ph[kLo16] = l;
+    } else {
+        ph[0] = make_uint4(0, 0, 0, 0);
+        ph[kLo16] = make_uint4(0, 0, 0, 0);
+    }
 }
+
+// Row-space accumulators of the output layer, one per epilogue warp (kRows floats): they overlay
+// planes 2 and 3, which are dead by then -- warps 0..7 in the hi planes, 8..15 in the lo planes.
+__device__ __forceinline__ float* priv_base(unsigned char* act, int ew) {
+    return reinterpret_cast<float*>(act + ((ew >> 3) * kLo16 + 2 * kPlane16) * 16) + (ew & 7) * kRows;
+}
+static_assert(8 * kRows * 4 <= 2 * kPlane16 * 16 && kEpiWarps <= 16, "per-warp accumulators must fit planes 2 and 3");
 
 struct TcParams {
     const unsigned char* wimg;   // weight image (global): per step, per unit, [2][rows][8] halfs
@@ -141,7 +177,28 @@ struct TcParams {
     long long total_rows;
     float* skip;                 // per-CTA scratch for the skip tensors
     unsigned int* flags;         // [0] bits of the largest |activation| stored as FP16, [1] protocol error
+    long long* trace;            // development aid (RCED_TC_TRACE): clock64 stamps of CTA 0's second batch, or null
 };
+// trace slots: [step][tile][event]; events: 0 MMA issue begins, 1 MMA issued (commit), 2 epilogue
+// past its waits, 3 accumulator in registers, 4 epilogue done (arrive); tile 0 only: 5 / 6 before /
+// after the wait for the step's weights
+__device__ __forceinline__ void stamp(long long* trace, bool on, int s, int t, int ev) {
+    if (on) trace[(s * kTiles + t) * kTraceEvents + ev] = clock64();
+}
+
+// what the epilogue of a conv step does, as data: one code body serves every layer (the
+// per-layer template instantiations of the first version were ~100 KB of code and missed the
+// instruction cache at the start of every step)
+struct EpiStep {
+    int np;        // accumulator column of the hi x Wlo block
+    int cg;        // groups of 8 output channels
+    int relu;
+    int add;       // 0 none, 1 before the ReLU, 2 after it (V3)
+    int add_base;  // first 8-channel group of the skip slot added
+    int save_base; // first 8-channel group of the skip slot saved (-1: none)
+    int pad0, pad1;
+};
+static_assert(sizeof(EpiStep) == 32, "EpiStep layout");
 
 struct Ctx {
     unsigned char* smem;
@@ -149,8 +206,11 @@ struct Ctx {
     uint32_t bars;      // shared address of the barrier block
     uint32_t tm;        // tensor-memory base
     const float* bias;  // shared copy
+    const EpiStep* epi; // shared copy
     const long long* bnd;
     unsigned int* err;
+    long long* trace;
+    bool tracing;
     int lane, quad, grp, et, nf;
     float* skip;
     float* priv;        // this warp's row-space accumulator of the (1,129) layer [kRows]
@@ -171,148 +231,148 @@ __device__ __forceinline__ void locate(const long long* __restrict__ row_off, in
 }
 
 // ------------------------------------------------------------------------------------------
-// epilogue of one conv layer for one row tile
+// epilogue of one conv layer for one row tile (runtime-parameterised, see EpiStep)
 // ------------------------------------------------------------------------------------------
-template <int ARCH, int LI>
-__device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int t, const uint32_t par, float& amax) {
-    constexpr LSpec S = spec(ARCH, LI);
-    constexpr int NP = step_np(ARCH, LI);
-    constexpr int CG = (S.cout + 7) / 8;
-    constexpr bool PRE = S.add >= 0 && !S.after;
-    constexpr bool POST = S.add >= 0 && S.after;
-    constexpr bool SAVE = S.save >= 0;
-
+__device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const int t, const uint32_t par, float& amax) {
+    const EpiStep e = c.epi[s];
     const int r = t * 128 + c.quad * 32 + c.lane;   // row in tile space
     const int fi = r / kFS, b = r - fi * kFS;
     const bool valid = fi < c.nf && b < kBins;
     const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
+    const float4* sp = reinterpret_cast<const float4*>(c.skip) + ((size_t)e.add_base * kRows + r) * 2;
+    float4* dp = reinterpret_cast<float4*>(c.skip) + ((size_t)(e.save_base < 0 ? 0 : e.save_base) * kRows + r) * 2;
 
     // the skip tensor (this thread's own row, written by this thread layers ago) does not depend
-    // on the accumulator: its L2 latency hides behind the wait for the MMAs
-    float4 sk[CG][2];
-#pragma unroll
-    for (int g = 0; g < CG; ++g) sk[g][0] = sk[g][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (S.add >= 0) {
-        const float4* sp = reinterpret_cast<const float4*>(c.skip) + ((size_t)skip_c8_base(ARCH, S.add >= 0 ? S.add : 0) * kRows + r) * 2;
-#pragma unroll
-        for (int g = 0; g < CG; ++g) {
-            sk[g][0] = sp[(size_t)g * kRows * 2];
-            sk[g][1] = sp[(size_t)g * kRows * 2 + 1];
-        }
+    // on the accumulator: the L2 latency of its first group hides behind the wait for the MMAs
+    float4 sk0 = make_float4(0.f, 0.f, 0.f, 0.f), sk1 = sk0;
+    if (e.add) {
+        sk0 = sp[0];
+        sk1 = sp[1];
     }
-
-    // accumulator of this tile complete; MMAs of the next tile (which read this tile's last rows
-    // as their halo) complete as well, so the planes can be overwritten in place
-    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 100 + LI);
-    if (t + 1 < kTiles) mbar_wait(bar_addr(c, kBarAccFull + t + 1), par, c.err, 200 + LI);
+    // Even and odd tiles are issued by two threads, each committing in its own order: this tile's
+    // accumulator is complete with acc_full[t]; the neighbour tile's commit (other thread) also
+    // covers that thread's earlier tile on the other side -- so nobody reads this tile's rows as
+    // a halo any more and the planes can be updated in place
+    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 100 + s);
+    mbar_wait(bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t - 1)), par, c.err, 200 + s);
     fence_after();
+    stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 2);
 
-    float d1[CG][8], d2[CG][8];
-#pragma unroll
-    for (int g = 0; g < CG; ++g) {
-        tmem_ld8(ta + g * 8, d1[g]);
-        tmem_ld8(ta + NP + g * 8, d2[g]);
-    }
-    tmem_wait_ld();
-#pragma unroll
-    for (int g = 0; g < CG; ++g) {
-        reg_fence8(d1[g]);
-        reg_fence8(d2[g]);
-    }
-    const float* bias = c.bias + LI * 32;
-#pragma unroll
-    for (int g = 0; g < CG; ++g) {
-        float v[8];
+    float d1[8], d2[8];
+    tmem_ld8(ta, d1);
+    tmem_ld8(ta + e.np, d2);
+    const float* bias = c.bias + s * 32;
+#pragma unroll 1
+    for (int g = 0; g < e.cg; ++g) {
+        tmem_wait_ld();
+        reg_fence8(d1);
+        reg_fence8(d2);
+        if (g == 0) stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 3);
         const float4 b0 = *reinterpret_cast<const float4*>(bias + g * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const float ss[8] = {sk[g][0].x, sk[g][0].y, sk[g][0].z, sk[g][0].w, sk[g][1].x, sk[g][1].y, sk[g][1].z, sk[g][1].w};
+        const float ss[8] = {sk0.x, sk0.y, sk0.z, sk0.w, sk1.x, sk1.y, sk1.z, sk1.w};
+        float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float x = (d1[g][e] + d2[g][e]) + bb[e];
-            if constexpr (PRE) x += ss[e];
-            if constexpr (S.relu) x = fmaxf(x, 0.f);
-            if constexpr (POST) x += ss[e];
-            x = valid ? x : 0.f;
-            amax = fmaxf(amax, fabsf(x));
-            v[e] = x;
+        for (int i = 0; i < 8; ++i) {
+            float x = (d1[i] + d2[i]) + bb[i];
+            if (e.add == 1) x += ss[i];
+            if (e.relu) x = fmaxf(x, 0.f);
+            if (e.add == 2) x += ss[i];
+            amax = fmaxf(amax, fabsf(x));   // (halo rows hold finite sums of their neighbours: harmless)
+            v[i] = x;
         }
-        if constexpr (SAVE) {
-            float4* dp = reinterpret_cast<float4*>(c.skip) + ((size_t)(skip_c8_base(ARCH, S.save >= 0 ? S.save : 0) + g) * kRows + r) * 2;
-            dp[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dp[1] = make_float4(v[4], v[5], v[6], v[7]);
+        // next group: accumulator columns and skip values are in flight while this one is stored
+        if (g + 1 < e.cg) {
+            tmem_ld8(ta + (g + 1) * 8, d1);
+            tmem_ld8(ta + e.np + (g + 1) * 8, d2);
+            if (e.add) {
+                sk0 = sp[(size_t)(g + 1) * kRows * 2];
+                sk1 = sp[(size_t)(g + 1) * kRows * 2 + 1];
+            }
         }
-        store_split8(c.act, g, kLead + r, v);
+        if (e.save_base >= 0) {
+            dp[(size_t)g * kRows * 2] = make_float4(v[0], v[1], v[2], v[3]);
+            dp[(size_t)g * kRows * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        store_split8(c.act, g, kLead + r, v, valid);
     }
     fence_before();       // tcgen05.ld of this accumulator ordered before the barrier
     fence_async_smem();   // plane writes visible to the tensor core (async proxy)
     __syncwarp();
     if (c.lane == 0) mbar_arrive(bar_addr(c, kBarActReady + t));
+    stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 4);
 }
 
 // Epilogue of one pass of the (1,129) layer for one row tile.  D[row r][tap] belongs to output
 // row r - tap + 64 (same frame only): the warp sums its 32 x 48 block along the diagonals with one
 // shuffle per tap -- lane m collects the diagonals d = tap - lane in {m - 32, m, m + 32} -- and adds
 // the three sums to its private row-space accumulator (no atomics, fixed summation order).
-template <int ARCH, int PASS>
-__device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const uint32_t par) {
-    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 300 + PASS);
+template <int ARCH>
+__device__ __forceinline__ void epi_final_tile(const Ctx& c, const int pass, const int t, const uint32_t par) {
+    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 300 + pass);
     fence_after();
+    stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, num_layers(ARCH) - 1 + pass, t, 2);
     const int r0 = t * 128 + c.quad * 32;
     const int r = r0 + c.lane;
     const int fi = r / kFS, b = r - fi * kFS;
     const bool valid = fi < c.nf && b < kBins;
     const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
-    float d[kFinalTaps / 8][8];
-#pragma unroll
-    for (int g = 0; g < kFinalTaps / 8; ++g) tmem_ld8(ta + g * 8, d[g]);
-    tmem_wait_ld();
-#pragma unroll
-    for (int g = 0; g < kFinalTaps / 8; ++g) reg_fence8(d[g]);
-    // tap = 48 PASS + i stays inside the frame iff 0 <= b - tap + 64 <= 128
-    const int ilo = valid ? b - 64 - PASS * kFinalTaps : 4096;
+    // tap = 48 pass + i stays inside the frame iff 0 <= b - tap + 64 <= 128
+    const int ilo = valid ? b - 64 - pass * kFinalTaps : 4096;
     float am = 0.f, a0 = 0.f, ap = 0.f;
+    float d[8];
+    tmem_ld8(ta, d);
+#pragma unroll 1
+    for (int g = 0; g < kFinalTaps / 8; ++g) {
+        tmem_wait_ld();
+        reg_fence8(d);
+        float v[8];
 #pragma unroll
-    for (int g = 0; g < kFinalTaps / 8; ++g)
+        for (int e = 0; e < 8; ++e) v[e] = (unsigned)(g * 8 + e - ilo) <= 128u ? d[e] : 0.f;
+        if (g + 1 < kFinalTaps / 8) tmem_ld8(ta + (g + 1) * 8, d);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int i = g * 8 + e;
-            const float v = (unsigned)(i - ilo) <= 128u ? d[g][e] : 0.f;
-            const float x = __shfl_sync(0xffffffffu, v, (i - c.lane) & 31);   // from lane l = (i - m) mod 32
-            if (i < 32) {
-                if (c.lane <= i) a0 += x; else am += x;        // d = m  |  d = m - 32
-            } else {
-                if (c.lane <= i - 32) ap += x; else a0 += x;   // d = m + 32  |  d = m
-            }
+            const float x = __shfl_sync(0xffffffffu, v[e], (i - c.lane) & 31);   // from lane l = (i - m) mod 32
+            const int q = (i - c.lane) >> 5;                                     // diagonal d = m + 32 q, q in {-1, 0, 1}
+            am += q < 0 ? x : 0.f;
+            a0 += q == 0 ? x : 0.f;
+            ap += q > 0 ? x : 0.f;
         }
-    // output row of diagonal d: r0 + 64 - 48 PASS - d
+    }
+    // output row of diagonal d: r0 + 64 - 48 pass - d
     float* pw = c.priv;
-    const int ro = r0 + 64 - PASS * kFinalTaps - c.lane;
+    const int ro = r0 + 64 - pass * kFinalTaps - c.lane;
     if (ro + 32 >= 0 && ro + 32 < kRows) pw[ro + 32] += am;
     if (ro >= 0 && ro < kRows) pw[ro] += a0;
     if (ro - 32 >= 0 && ro - 32 < kRows) pw[ro - 32] += ap;
     fence_before();
     __syncwarp();
     if (c.lane == 0) mbar_arrive(bar_addr(c, kBarActReady + t));
+    stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, num_layers(ARCH) - 1 + pass, t, 4);
 }
 
-template <int ARCH, int STEP>
+// all steps of one batch for this epilogue warp
+template <int ARCH>
 __device__ __forceinline__ void epi_steps(const Ctx& c, const uint32_t k0, float& amax) {
-    if constexpr (STEP < n_steps(ARCH)) {
-        const uint32_t par = (k0 + STEP) & 1;
-        if constexpr (STEP == num_layers(ARCH) - 1) {
-            // planes 2 and 3 are dead once the MMAs of the last conv layer have completed (both
-            // groups have seen acc_full of its last tile: group 0 as the halo condition of tile 6,
-            // group 1 for tile 7): they now hold the per-warp accumulators of the output layer
-            for (int i = c.lane; i < kRows / 4; i += 32) reinterpret_cast<float4*>(c.priv)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();
-        }
+    constexpr int NL = num_layers(ARCH);
 #pragma unroll 1
-        for (int t = c.grp; t < kTiles; t += 2) {
-            if constexpr (is_final(ARCH, STEP)) epi_final_tile<ARCH, STEP - (num_layers(ARCH) - 1)>(c, t, par);
-            else epi_conv_tile<ARCH, STEP>(c, t, par, amax);
-        }
-        epi_steps<ARCH, STEP + 1>(c, k0, amax);
+    for (int s = 0; s < NL - 1; ++s) {
+        const uint32_t par = (k0 + s) & 1;
+#pragma unroll 1
+        for (int t = c.grp; t < kTiles; t += kGroups) epi_conv_tile(c, s, t, par, amax);
+    }
+    // planes 2 and 3 are dead once the MMAs of the last conv layer have completed: they now hold
+    // the per-warp accumulators of the output layer
+    mbar_wait(bar_addr(c, kBarConvDone), (uint32_t)(k0 / n_steps(ARCH)) & 1, c.err, 400);
+    for (int i = c.lane; i < kRows / 4; i += 32) reinterpret_cast<float4*>(c.priv)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+#pragma unroll 1
+    for (int pass = 0; pass < kFinalPasses; ++pass) {
+        const uint32_t par = (k0 + NL - 1 + pass) & 1;
+#pragma unroll 1
+        for (int t = c.grp; t < kTiles; t += kGroups) epi_final_tile<ARCH>(c, pass, t, par);
     }
 }
 
@@ -339,6 +399,21 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     // ---- one-time setup ----------------------------------------------------------------------
     for (int i = threadIdx.x; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < NS * 32; i += kThreads) s_bias[i] = p.bias[i];
+    EpiStep* s_epi = reinterpret_cast<EpiStep*>(smem + smem_epi_off(ARCH));
+    if (threadIdx.x < NL - 1) {
+        const int li = threadIdx.x;
+        const LSpec sp = spec(ARCH, li);
+        EpiStep e;
+        e.np = step_np(ARCH, li);
+        e.cg = (sp.cout + 7) / 8;
+        e.relu = sp.relu;
+        e.add = sp.add < 0 ? 0 : (sp.after ? 2 : 1);
+        e.add_base = sp.add < 0 ? 0 : skip_c8_base(ARCH, sp.add);
+        e.save_base = sp.save < 0 ? -1 : skip_c8_base(ARCH, sp.save);
+        e.pad0 = e.pad1 = 0;
+        s_epi[li] = e;
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kFlagSlot) = 0u;
     for (int s = 0; s < NS; ++s) {
         const int nu = step_units(ARCH, s), nc = step_chunks(ARCH, s), ub = unit_base(ARCH, s);
         for (int u = threadIdx.x; u < nu; u += kThreads) {
@@ -356,9 +431,10 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars + 8 * (kBarWFull + i), 1);
-            mbar_init(bars + 8 * (kBarWFree + i), 1);
+            mbar_init(bars + 8 * (kBarWFree + i), 2);   // both issuing threads commit
         }
         mbar_init(bars + 8 * kBarInReady, kEpiWarps);
+        mbar_init(bars + 8 * kBarConvDone, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -372,59 +448,82 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     const uint32_t tm = s_tmem;
     const long long NB = (p.total_rows + kFB - 1) / kFB;
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 3) {
         // ================= MMA issue =================
-        const uint32_t act16 = smem_u32(act) >> 4;
-        uint32_t it = 0;
-        for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
-            mbar_wait(bars + 8 * kBarInReady, it & 1, err, 1);
+        // Two issuing threads (one elected lane of warp 0 and of warp 3) take the even and the odd row
+        // tiles: the tensor pipe accepts only a couple of instructions ahead of execution, so a
+        // single thread's work between two tiles (dependency check, descriptor set-up, commit) left
+        // the pipe idle; with two threads one prepares its tile while the other one issues.
+        // Per step the start-address words of every unit's A and B descriptors are built once into
+        // registers (fully unrolled, kMaxUnits slots): issuing a unit is an add and the MMA pair.
+        const int t_first = warp == 0 ? 0 : 1;
+        if (elect_one()) {
+            const uint32_t act16 = smem_u32(act) >> 4;
+            const uint32_t flag = bars + 8 * kFlagSlot;
+            uint32_t seen = 0;   // last value read from the scout's counter
+            uint32_t it = 0;
+            for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
+                const bool tr = p.trace != nullptr && blockIdx.x == 0 && it == 1;
 #pragma unroll 1
-            for (int s = 0; s < NS; ++s) {
-                const uint32_t k = it * NS + s;
-                const int wb = k & 1;
-                mbar_wait(bars + 8 * (kBarWFull + wb), (k >> 1) & 1, err, 2);
-                const int4 st = steps[s];
-                const int nu = st.x, np = st.z, tile16 = st.w & 0xFFFF;
-                const bool fin = (st.w >> 16) != 0;
-                const int2* ut = tab + st.y;
-                const uint32_t w16 = smem_u32(smem + smem_w_off(ARCH, wb)) >> 4;
-                const uint32_t id_a = idesc_f16(fin ? np : 2 * np), id_b = idesc_f16(np);
-                const uint32_t b_lbo = (uint32_t)(2 * np) << 16;   // LBO of the B tile: rows per chunk x 16 bytes
-#pragma unroll 1
-                for (int t = 0; t < kTiles; ++t) {
-                    if (s > 0) {
-                        const uint32_t pp = (k - 1) & 1;
-                        if (t == 0) mbar_wait(bars + 8 * (kBarActReady + 0), pp, err, 3);
-                        if (t + 1 < kTiles) mbar_wait(bars + 8 * (kBarActReady + t + 1), pp, err, 4);
+                for (int s = 0; s < NS; ++s) {
+                    const uint32_t k = it * NS + s;
+                    const int wb = k & 1;
+                    const int4 st = steps[s];
+                    const int nu = st.x, np = st.z, tile16 = st.w & 0xFFFF;
+                    const bool fin = (st.w >> 16) != 0;
+                    const int2* ut = tab + st.y;
+                    const uint32_t w16 = smem_u32(smem + smem_w_off(ARCH, wb)) >> 4;
+                    const uint32_t id_a = idesc_f16(fin ? np : 2 * np), id_b = idesc_f16(np);
+                    const uint32_t b_lbo = (uint32_t)(2 * np) << 16;   // LBO of the B tile: rows per chunk x 16 bytes
+                    uint32_t ua[kMaxUnits], ub[kMaxUnits];
+#pragma unroll
+                    for (int u = 0; u < kMaxUnits; ++u) {
+                        const int2 e = ut[u < nu ? u : 0];
+                        ua[u] = ((act16 + kLead + (uint32_t)e.x) & 0x3FFFu) | ((uint32_t)e.y << 16);
+                        ub[u] = ((w16 + (uint32_t)(u * tile16)) & 0x3FFFu) | b_lbo;
                     }
-                    fence_after();
-                    if (elect_one()) {
-                        const uint32_t d = tm + (uint32_t)(t * kAccCols);
-                        const uint32_t a0 = act16 + kLead + 128 * t;
-#pragma unroll 2
-                        for (int u = 0; u < nu; ++u) {
-                            const int2 e = ut[u];
-                            const uint32_t a_lo32 = ((a0 + (uint32_t)e.x) & 0x3FFFu) | ((uint32_t)e.y << 16);
-                            const uint32_t b_lo32 = ((w16 + (uint32_t)(u * tile16)) & 0x3FFFu) | b_lbo;
-                            const uint64_t da_hi = make_desc(a_lo32), da_lo = make_desc(a_lo32 + kLo16);
-                            const uint64_t db = make_desc(b_lo32);
-                            if (!fin) {
-                                umma_f16(d, da_hi, db, id_a, u > 0);      // hi x [Whi | Wlo] -> columns [0, 2 NP)
-                                umma_f16(d, da_lo, db, id_b, 1);          // lo x Whi        -> columns [0, NP)
-                            } else {
-                                umma_f16(d, da_hi, db, id_a, u > 0);      // hi x Whi (48 taps)
-                                umma_f16(d, da_lo, db, id_a, 1);          // lo x Whi
-                                umma_f16(d, da_hi, make_desc(b_lo32 + (uint32_t)np), id_a, 1);   // hi x Wlo (rows 48..95)
-                            }
+#pragma unroll 1
+                    for (int t = t_first; t < kTiles; t += 2) {
+                        // the scout (warp 2) has waited on this tile's mbarriers and published its index: a
+                        // shared-memory load costs ~30 cycles where an mbarrier test costs ~160 (umma_probe
+                        // lat), and it is only needed when the last value seen does not cover this tile
+                        stamp(p.trace, tr, s, t, 5);
+                        const uint32_t need = k * kTiles + t + 1;
+                        for (int spin = 0; seen < need; ++spin) {
+                            seen = ld_acquire(flag);
+                            if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
                         }
+                        fence_after();
+                        stamp(p.trace, tr, s, t, 0);
+                        const uint32_t d = tm + (uint32_t)(t * kAccCols);
+                        const uint32_t toff = 128u * t;   // never carries out of the 14-bit start field
+                        if (!fin) {
+#pragma unroll
+                            for (int u = 0; u < kMaxUnits; ++u) {
+                                if (u < nu) {
+                                    const uint64_t db = make_desc(ub[u]);
+                                    umma_f16(d, make_desc(ua[u] + toff), db, id_a, u > 0);     // hi x [Whi | Wlo] -> columns [0, 2 NP)
+                                    umma_f16(d, make_desc(ua[u] + toff + kLo16), db, id_b, 1); // lo x Whi        -> columns [0, NP)
+                                    if (u == 0) stamp(p.trace, tr, s, t, 6);
+                                }
+                            }
+                        } else {
+                            // output layer pass: one unit; hi x Whi, lo x Whi, hi x Wlo (rows 48..95 of the tile)
+                            const uint64_t db = make_desc(ub[0]);
+                            umma_f16(d, make_desc(ua[0] + toff), db, id_a, 0);
+                            umma_f16(d, make_desc(ua[0] + toff + kLo16), db, id_a, 1);
+                            umma_f16(d, make_desc(ua[0] + toff), make_desc(ub[0] + (uint32_t)np), id_a, 1);
+                        }
+                        stamp(p.trace, tr, s, t, 7);
                         umma_commit(bars + 8 * (kBarAccFull + t));
+                        stamp(p.trace, tr, s, t, 1);
                     }
-                    __syncwarp();
+                    umma_commit(bars + 8 * (kBarWFree + wb));
+                    if (s == NL - 2) umma_commit(bars + 8 * kBarConvDone);
                 }
-                if (elect_one()) umma_commit(bars + 8 * (kBarWFree + wb));
-                __syncwarp();
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ================= weight producer =================
         uint32_t it = 0;
@@ -445,6 +544,33 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 __syncwarp();
             }
         }
+    } else if (warp == 2) {
+        // ================= dependency scout =================
+        // Waits, in the MMA thread's issue order, on the mbarriers every (step, tile) depends on and
+        // publishes the number of tiles cleared for issue.
+        if (elect_one()) {
+            const uint32_t flag = bars + 8 * kFlagSlot;
+            uint32_t done = 0;
+            uint32_t it = 0;
+            for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
+#pragma unroll 1
+                for (int s = 0; s < NS; ++s) {
+                    const uint32_t k = it * NS + s;
+                    const int wb = k & 1;
+#pragma unroll 1
+                    for (int t = 0; t < kTiles; ++t) {
+                        if (t == 0) {
+                            if (s == 0) mbar_wait(bars + 8 * kBarInReady, it & 1, err, 1);
+                            mbar_wait(bars + 8 * (kBarWFull + wb), (k >> 1) & 1, err, 2);
+                            if (s > 0) mbar_wait(bars + 8 * (kBarActReady + 0), (k - 1) & 1, err, 3);
+                        }
+                        if (s > 0 && t + 1 < kTiles) mbar_wait(bars + 8 * (kBarActReady + t + 1), (k - 1) & 1, err, 4);
+                        st_release(flag, ++done);
+                    }
+                }
+            }
+        }
+        __syncwarp();
     } else if (warp >= kCtrlWarps) {
         // ================= epilogue groups =================
         Ctx c;
@@ -453,14 +579,17 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         c.bars = bars;
         c.tm = tm;
         c.bias = s_bias;
+        c.epi = s_epi;
         c.bnd = bnd;
         c.err = err;
+        c.trace = p.trace;
+        c.tracing = false;
         c.lane = lane;
         c.quad = warp & 3;
-        c.grp = (warp - kCtrlWarps) >> 2;
+        c.grp = (warp - kCtrlWarps) >> 2;   // four consecutive warps cover the four lane quadrants
         c.et = (warp - kCtrlWarps) * 32 + lane;
         c.skip = p.skip + (size_t)blockIdx.x * skip_floats_per_cta(ARCH);
-        c.priv = reinterpret_cast<float*>(act + 2 * kPlane16 * 16) + (warp - kCtrlWarps) * kRows;
+        c.priv = priv_base(act, warp - kCtrlWarps);
         float amax = 0.f;
         const float bias_f = s_bias[(NL - 1) * 32];
         uint32_t it = 0;
@@ -469,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             const long long left = p.total_rows - g0;
             c.nf = left < kFB ? (int)left : kFB;
             c.g0 = g0;
+            c.tracing = p.trace != nullptr && blockIdx.x == 0 && it == 1;
             if (c.et < kFB) {
                 long long lo = 0, hi = 0;
                 if (c.et < c.nf) locate(p.row_off, p.n_utt, g0 + c.et, lo, hi);
@@ -478,8 +608,8 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             epi_bar();   // bounds visible; every MMA of the previous batch has completed (its epilogues waited)
             // the output layer's accumulators of the previous batch overlaid planes 2 and 3 (hi),
             // halo rows included: those must read as zero again before any tap touches them
-            if (it > 0 && c.et < 2 * 16) {
-                const int pl = 2 + (c.et >> 4), hr = c.et & 15;
+            if (it > 0 && c.et < 4 * 16) {
+                const int pl = 2 + ((c.et >> 4) & 1) + (c.et >> 5) * kPlanes, hr = c.et & 15;   // planes 2, 3 of hi and lo
                 const int row = hr < 8 ? hr : kLead + kRows + (hr - 8);
                 reinterpret_cast<uint4*>(act)[pl * kPlane16 + row] = make_uint4(0, 0, 0, 0);
             }
@@ -501,22 +631,21 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
 #pragma unroll
                     for (int tt = 0; tt < 8; ++tt) v[tt] = 0.f;
                 }
-                store_split8(act, 0, kLead + r, v);
+                store_split8(act, 0, kLead + r, v, true);
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + 8 * kBarInReady);
 
-            epi_steps<ARCH, 0>(c, it * NS, amax);
+            epi_steps<ARCH>(c, it * NS, amax);
 
             epi_bar();   // every warp's partial sums of the output layer are complete
             {
-                const float* pw = reinterpret_cast<const float*>(act + 2 * kPlane16 * 16);
                 for (int i = c.et; i < c.nf * kBins; i += 32 * kEpiWarps) {
                     const int fi = i / kBins, b = i - fi * kBins;
                     float acc = 0.f;
 #pragma unroll
-                    for (int w = 0; w < kEpiWarps; ++w) acc += pw[w * kRows + fi * kFS + b];
+                    for (int w = 0; w < kEpiWarps; ++w) acc += priv_base(act, w)[fi * kFS + b];
                     p.out[(g0 + fi) * kBins + b] = acc + bias_f;
                 }
             }
@@ -608,8 +737,10 @@ static cudaError_t launch_tc_t(const tc::TcParams& p, int num_sms, cudaStream_t 
     return cudaGetLastError();
 }
 
+int tc_trace_slots(int arch) { return tc::n_steps(arch) * tc::kTiles * tc::kTraceEvents; }
+
 cudaError_t launch_net_tc(int arch, const NetParams& np, const unsigned char* wimg, const float* bias, float* skip,
-                          unsigned int* flags, int num_sms, cudaStream_t stream) {
+                          unsigned int* flags, long long* trace, int num_sms, cudaStream_t stream) {
     tc::TcParams p;
     p.wimg = wimg;
     p.bias = bias;
@@ -620,6 +751,7 @@ cudaError_t launch_net_tc(int arch, const NetParams& np, const unsigned char* wi
     p.total_rows = np.total_rows;
     p.skip = skip;
     p.flags = flags;
+    p.trace = trace;
     switch (arch) {
         case 1: return launch_tc_t<1>(p, num_sms, stream);
         case 2: return launch_tc_t<2>(p, num_sms, stream);

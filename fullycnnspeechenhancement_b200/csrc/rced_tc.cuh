@@ -29,9 +29,11 @@ constexpr int kActBytes = 2 * kPlanes * kPlane16 * 16;
 constexpr int kAccCols = 64;                  // tensor-memory columns per tile
 constexpr int kFinalTaps = 48;                // taps of the (1,129) layer per pass (N of the pass)
 constexpr int kFinalPasses = 3;
-constexpr int kCtrlWarps = 4;                 // warp 0: MMA issue, warp 1: weight producer, 2-3: idle
-constexpr int kEpiWarps = 8;                  // two groups of four (one per tensor-memory lane quadrant)
+constexpr int kCtrlWarps = 4;                 // warps 0 / 3: MMA issue of the even / odd row tiles, 1: weight producer, 2: dependency scout
+constexpr int kEpiWarps = 16;                 // groups of four warps (one per tensor-memory lane quadrant)
+constexpr int kGroups = kEpiWarps / 4;        // group g takes the row tiles t = g, g + kGroups, ...
 constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
+constexpr int kTraceEvents = 8;               // clock stamps per (step, tile) of the development trace
 constexpr int kOutStride = 132;               // floats per frame of the output accumulator
 
 static_assert(kFB * kFS <= kRows, "frames of a batch must fit the row tiles");
@@ -73,6 +75,14 @@ RCED_HD constexpr int unit_base(int arch, int s) {
     return o;
 }
 RCED_HD constexpr int total_units(int arch) { return unit_base(arch, n_steps(arch)); }
+RCED_HD constexpr int max_units(int arch) {
+    int m = 0;
+    for (int i = 0; i < n_steps(arch); ++i)
+        if (step_units(arch, i) > m) m = step_units(arch, i);
+    return m;
+}
+constexpr int kMaxUnits = 18;   // register slots of the MMA issue loop
+static_assert(max_units(1) <= kMaxUnits && max_units(2) <= kMaxUnits && max_units(3) <= kMaxUnits, "raise kMaxUnits");
 
 // A-operand addressing of chunk c of step s, in 16-byte units relative to row (kLead + 128 t)
 // of plane 0: channel group g = c / kw lives in plane g, tap j = c % kw reads rows shifted by j - pad
@@ -105,7 +115,8 @@ RCED_HD constexpr int smem_bias_off(int arch) { return smem_step_off(arch) + pad
 RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 128 * n_steps(arch); }             // float[kFB][kOutStride]
 RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + pad128(4 * kFB * kOutStride); }     // long long[kFB][2]
 RCED_HD constexpr int smem_bar_off(int arch) { return smem_bnd_off(arch) + 128; }                              // mbarriers
-RCED_HD constexpr int smem_total(int arch) { return smem_bar_off(arch) + 256; }
+RCED_HD constexpr int smem_epi_off(int arch) { return smem_bar_off(arch) + 256; }                             // EpiStep[n_steps]
+RCED_HD constexpr int smem_total(int arch) { return smem_epi_off(arch) + 32 * n_steps(arch); }
 
 // mbarrier slots (8 bytes each) inside the barrier block
 constexpr int kBarAccFull = 0;     // [kTiles]  tcgen05.commit after the last MMA of (step, tile)
@@ -113,6 +124,8 @@ constexpr int kBarActReady = 8;    // [kTiles]  epilogue of (step, tile) done (p
 constexpr int kBarWFull = 16;      // [2]       weights of a step landed in buffer b
 constexpr int kBarWFree = 18;      // [2]       MMAs reading buffer b complete
 constexpr int kBarInReady = 20;    //           layer-0 input of the batch staged
+constexpr int kBarConvDone = 21;   //           every MMA of the batch's last conv layer complete
+constexpr int kFlagSlot = 24;      //           u32 progress counter published by the dependency scout
 
 }  // namespace tc
 }  // namespace rced

@@ -286,6 +286,8 @@ struct RateArgs {
     int store_warps;   // warps 1.. that stream 16-byte shared stores while the MMAs run
     int layout;     // 0: no swizzle (chunk planes), 2: 128-byte swizzle (row = 128 B)
     int same_a;     // 1: every instruction reads the same A tile (no tap / tile cycling)
+    int commit_every;   // > 0: tcgen05.commit (to a barrier nobody waits on) after every so many MMAs
+    int fence_every;    // > 0: tcgen05.fence::after_thread_sync after every so many MMAs
     long long* cycles;   // per CTA
     int* status;
 };
@@ -297,11 +299,13 @@ template <int KIND>
 __global__ void __launch_bounds__(256, 1) rate_kernel(RateArgs p) {
     extern __shared__ uint32_t sm_raw[];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bar2;
     __shared__ uint32_t s_tmem;
     __shared__ volatile int s_stop;
     const uint32_t base = (smem_u32(sm_raw) + 1023u) & ~1023u;
     uint32_t* sA = sm_raw + (base - smem_u32(sm_raw)) / 4;
     uint32_t* sB = sA + kRateABytes / 4;
+    if (threadIdx.x == 0) mbar_init(smem_u32(&bar2), 1);
     uint32_t* sS = sB + kRateBBytes / 4;   // 16 KB scratch for the store warps
     for (int i = threadIdx.x; i < (kRateABytes + kRateBBytes + 16384) / 4; i += blockDim.x) sA[i] = 0;
     if (threadIdx.x == 0) {
@@ -337,9 +341,14 @@ __global__ void __launch_bounds__(256, 1) rate_kernel(RateArgs p) {
         }
         const long long t0 = clock64();
         if (elect_one()) {
+            int since_c = 0, since_f = 0;
             for (int i = 0; i < p.ni; i += 16) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) umma<KIND>(dd[j], da[j], db[j], idesc, 1);
+                for (int j = 0; j < 16; ++j) {
+                    umma<KIND>(dd[j], da[j], db[j], idesc, 1);
+                    if (p.commit_every > 0 && ++since_c == p.commit_every) { umma_commit(smem_u32(&bar2)); since_c = 0; }
+                    if (p.fence_every > 0 && ++since_f == p.fence_every) { fence_after(); since_f = 0; }
+                }
             }
             umma_commit(smem_u32(&bar));
         }
@@ -385,7 +394,7 @@ static void run_rate(int grid) {
                 for (int sw = 0; sw <= 4; sw += 4)
                     for (int n : ns) {
                         if ((same || sw) && (n != 32 && n != 128)) continue;
-                        RateArgs a{n, m, 4096, sw, layout, same, dc, ds};
+                        RateArgs a{n, m, 4096, sw, layout, same, 0, 0, dc, ds};
                         rate_kernel<KIND><<<grid, 256, smem>>>(a);
                         cudaError_t e = cudaDeviceSynchronize();
                         if (e != cudaSuccess) {
@@ -439,6 +448,26 @@ __global__ void __launch_bounds__(128, 1) ld_kernel(long long* cycles, float* si
     if (threadIdx.x < 32) tmem_dealloc(s_tmem, 512);
 }
 
+static void run_sync_sweep() {
+    const size_t smem = kRateABytes + kRateBBytes + 16384 + 1024;
+    CK(cudaFuncSetAttribute(rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long* dc;
+    int* ds;
+    CK(cudaMalloc(&dc, 8));
+    CK(cudaMalloc(&ds, 4));
+    CK(cudaMemset(ds, 0, 4));
+    for (int n : {32, 64})
+        for (int ce : {0, 32, 16, 8, 4, 2})
+            for (int fe : {0, 8}) {
+                RateArgs a{n, 128, 4096, 0, 0, 0, ce, fe, dc, ds};
+                rate_kernel<0><<<1, 256, smem>>>(a);
+                CK(cudaDeviceSynchronize());
+                long long c;
+                CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
+                printf("sync f16 N %3d commit every %2d MMAs, fence every %d: %6.1f cycles/MMA\n", n, ce, fe, (double)c / 4096);
+            }
+}
+
 static void run_ld() {
     long long* dc;
     float* dsink;
@@ -455,6 +484,89 @@ static void run_ld() {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// lat: cost of the synchronisation primitives the MMA-issuing thread executes between two tiles
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) lat_kernel(long long* out) {
+    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ volatile int flag;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bar[0]), 1);
+        mbar_init(smem_u32(&bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        flag = 1;
+    }
+    if (threadIdx.x < 32) tmem_alloc(smem_u32(&s_tmem), 32);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    if (threadIdx.x == 0) {
+        // complete phase 0 of bar[0] so that waits on parity 0 succeed at once
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[0])) : "memory");
+        long long t0 = clock64();
+        for (int i = 0; i < 64; ++i) mbar_wait(smem_u32(&bar[0]), 0);
+        long long t1 = clock64();
+        out[0] = (t1 - t0) / 64;   // try_wait on a completed phase
+        t0 = clock64();
+        for (int i = 0; i < 64; ++i) fence_after();
+        t1 = clock64();
+        out[1] = (t1 - t0) / 64;   // tcgen05.fence::after_thread_sync
+        t0 = clock64();
+        int acc = 0;
+        for (int i = 0; i < 64; ++i) acc += flag;
+        t1 = clock64();
+        out[2] = (t1 - t0) / 64 + (acc == 12345);   // volatile shared load
+        // commit with nothing outstanding -> wait for it
+        t0 = clock64();
+        for (int i = 0; i < 16; ++i) {
+            umma_commit(smem_u32(&bar[1]));
+            mbar_wait(smem_u32(&bar[1]), i & 1);
+        }
+        t1 = clock64();
+        out[3] = (t1 - t0) / 16;   // commit + wait round trip
+        t0 = clock64();
+        for (int i = 0; i < 16; ++i) umma_commit(smem_u32(&bar[1]));
+        t1 = clock64();
+        out[4] = (t1 - t0) / 16;   // commit issue cost
+        t0 = clock64();
+        for (int i = 0; i < 64; ++i) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[0])) : "memory");
+        t1 = clock64();
+        out[5] = (t1 - t0) / 64;   // mbarrier.arrive
+        t0 = clock64();
+        for (int i = 0; i < 64; ++i) fence_async_smem();
+        t1 = clock64();
+        out[6] = (t1 - t0) / 64;   // fence.proxy.async.shared::cta
+        t0 = clock64();
+        int okc = 0;
+        for (int i = 0; i < 64; ++i) {
+            uint32_t ok;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(&bar[1])), "r"(1u) : "memory");
+            okc += ok;
+            if (!ok) break;
+        }
+        t1 = clock64();
+        out[7] = (t1 - t0) / 64 + (okc == 12345);   // mbarrier.test_wait (dependent chain)
+    }
+    fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(s_tmem, 32);
+}
+
+static void run_lat() {
+    long long* d;
+    CK(cudaMalloc(&d, 64));
+    lat_kernel<<<1, 128>>>(d);
+    CK(cudaDeviceSynchronize());
+    long long h[8];
+    CK(cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost));
+    const char* names[8] = {"mbarrier.try_wait (phase already complete)", "tcgen05.fence::after_thread_sync", "ld.volatile.shared",
+                            "tcgen05.commit + wait (nothing outstanding)", "tcgen05.commit (issue only)", "mbarrier.arrive",
+                            "fence.proxy.async.shared::cta", "mbarrier.test_wait (phase already complete)"};
+    for (int i = 0; i < 8; ++i) printf("lat %-48s %5lld cycles\n", names[i], h[i]);
+}
+
 int main(int argc, char** argv) {
     const char* mode = argc > 1 ? argv[1] : "check";
     if (!strcmp(mode, "check")) {
@@ -467,6 +579,14 @@ int main(int argc, char** argv) {
         const int grid = argc > 2 ? atoi(argv[2]) : 1;
         run_rate<2>(grid);
         run_rate<0>(grid);
+        return 0;
+    }
+    if (!strcmp(mode, "sync")) {
+        run_sync_sweep();
+        return 0;
+    }
+    if (!strcmp(mode, "lat")) {
+        run_lat();
         return 0;
     }
     if (!strcmp(mode, "ld")) {
