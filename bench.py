@@ -30,7 +30,7 @@ SAMPLE_RATE = 8000
 POOL = 64                    # distinct synthetic utterances, tiled to N_UTT
 METRIC = "R-CED V2 audio-seconds enhanced per second"
 UNIT = "audio-s/s"
-DEFAULT_VARIANT = "ffma"     # network kernel timed by default
+DEFAULT_VARIANT = "tc"       # network kernel timed by default: tcgen05 tensor cores, FP16 x3 split
 
 
 def synth_pool():
@@ -171,6 +171,67 @@ def reference_arm(args, rank, world):
     })
 
 
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written) or the fallback B200_PROFILING.md states."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(path))
+        return {"hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    except (OSError, ValueError):
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)"}
+
+
+def roofline(variant, achieved, ffma_peak, flops_valid, k2_ms, share, traffic, rows, tc_status):
+    """Roofline object of the dominant kernel (the fused network).  `achieved` is algorithmic:
+    valid-tap MACs x 2 per launch / mean launch time measured with CUDA events in the timed steps."""
+    common = {"achieved": achieved, "unit": "TFLOP/s", "flops_per_launch": flops_valid,
+              "flop_basis": "valid-tap MACs x2 (3,959,092 MAC/frame), FP32-equivalent", "kernel_ms": k2_ms,
+              "kernel_share_of_step": share}
+    if variant != "tc":
+        common.update({"bound": "fp32_ffma", "kernel": "rced_net_kernel<2,TMEM> (fused 16-layer network)", "peak": ffma_peak,
+                       "frac": achieved / ffma_peak, "traffic": traffic,
+                       "peak_source": "measured in this run by rced_ffma_peak (independent FFMA chains, 64 warps/SM); "
+                                      "MEASURED_PEAKS.json holds no FP32 figure; nominal 2*128*148*1.965 GHz = 74.4"})
+        return common
+    pk = measured_peaks()
+    # tensor-core work actually issued (DESIGN.md section 4): per 128-row tile and unit (two (tap, 8-channel) chunks,
+    # K = 16) A_hi x [Whi|Wlo] (N = 2 NP) and A_lo x Whi (N = NP); 8 tiles per 7-frame batch; output layer 3 passes
+    import ctypes as ct
+    from fullycnnspeechenhancement_b200 import _lib
+    out = (ct.c_int64 * 4096)()
+    _lib.check(_lib.lib().rced_tc_layout(2, out, 4096))
+    ns = out[0]
+    mac_tile, cyc_tile = 0, 0.0
+    for st in range(ns):
+        units, npad, final = out[12 + 6 * st], out[14 + 6 * st], out[17 + 6 * st]
+        if final:
+            mac_tile += units * 3 * 128 * npad * 16
+            cyc_tile += units * 3 * (32 + npad / 4.0)
+        else:
+            mac_tile += units * 128 * 16 * 3 * npad
+            cyc_tile += units * ((32 + 2 * npad / 4.0) + (32 + npad / 4.0))
+    batches = (rows + 6) // 7
+    issued = 2.0 * mac_tile * 8 * batches
+    common.update({
+        "bound": "tensor", "kernel": "rced_net_tc_kernel<2> (fused 16-layer network, tcgen05 kind::f16)",
+        "peak": pk["bf16_tflops"], "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", dense bf16/fp16",
+        "traffic": None,
+        "issued_tflops": issued / (k2_ms * 1e-3) / 1e12,
+        "issued_note": "tensor-core FLOP actually issued: 3 FP16 products per multiply, channels padded to 8 / 16 / 32, "
+                       "136-row frame stride, 7 frames per 8 row tiles",
+        "fp32_ffma_peak": ffma_peak, "achieved_vs_fp32_ffma_peak": achieved / ffma_peak,
+        "operand_fetch_model": {
+            "note": "a small-N tcgen05.mma is bound by its shared-memory operand fetch (32 + N/4 cycles at M = 128, "
+                    "profiles/r01_umma_probe_rates.log), not by the tensor pipe: the kernel's own ceiling is the sum of "
+                    "those cycles",
+            "mma_cycles_per_batch": cyc_tile * 8,
+            "pipe_busy_frac": cyc_tile * 8 * batches / 148.0 / (k2_ms * 1e-3 * 1.965e9)},
+        "guard": tc_status,
+    })
+    return common
+
+
 _REAL_STDOUT = None
 
 
@@ -228,7 +289,7 @@ def main():
 
     # random-init weights of the reference architecture (no checkpoint ships with the reference)
     weights = fold.glorot_weights(NET_WORK, seed=0)
-    eng = Enhancer(NET_WORK, weights, device=local_rank)
+    eng = Enhancer(NET_WORK, weights, device=local_rank, variant=args.variant)
     if args.skip_in_global:
         eng.set_skip_in_tmem(False)
     eng.set_variant(args.variant)
@@ -324,6 +385,10 @@ def main():
 
     flops_valid = 2.0 * lib.rced_mac_per_frame(eng.arch, 1) * rows
     achieved = flops_valid / (k2_ms * 1e-3) / 1e12
+    tc_status = None
+    if args.variant == "tc":
+        amax, perr = eng.tc_status()
+        tc_status = {"max_abs_activation": amax, "protocol_error": perr, "ffma_fallback_ran": bool(amax > 65504.0 or perr != 0)}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k2_dram_traffic.json")
     if os.path.exists(tpath):
@@ -334,26 +399,26 @@ def main():
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic (64 seeded tone/chirp + white/babble-noise utterances tiled to 1024 per GPU)",
+        "dtype": "f16x3 (FP16 hi/lo split, 3 products per multiply, FP32 accumulate; 1e-6 of float64)" if args.variant == "tc" else "f32",
+        "data": "synthetic (64 seeded tone/chirp + white/babble-noise utterances tiled to 1024 per GPU)",
         "config": {"workload": "R-CED V2 (FullyCNNV2, 16 layers, random-init Glorot weights) batched enhancement of "
                                "1024 synthetic 4 s 8 kHz utterances per B200 (BASELINE.json configs[1])",
                    "utterances_per_gpu": N_UTT, "samples_per_utterance": UTT_SAMPLES, "frames_per_gpu": rows,
                    "partition": "independent utterances per rank, no collective",
                    "l2": "per-step working set (131 MB wav in, 131 MB mag, 263 MB phase, 131 MB pred, 131 MB wav out) "
                          "exceeds the 126 MB L2, no explicit flush",
-                   "skip_storage": "global" if args.skip_in_global else "tmem"},
+                   "network_kernel": "tcgen05 tensor cores, FP16 x3 error-compensated split (rced_net_tc_kernel); FP32 FFMA "
+                                     "kernel queued behind it as range-guard fall-back" if args.variant == "tc"
+                                     else "FP32 FFMA (rced_net_kernel)",
+                   "skip_storage": ("global scratch (L2)" if args.variant == "tc" else
+                                    "global" if args.skip_in_global else "tmem")},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": total * 4,
                 "api": "Enhancer.run_plan_host: pinned host waveforms -> H2D -> rced_enhance (K1,K2,K3) -> D2H, "
                        "128-utterance chunks over 3 streams"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "fp32_ffma", "kernel": "rced_net_kernel<2,TMEM> (fused 16-layer network)",
-                     "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s", "frac": achieved / ffma_peak,
-                     "peak_source": "measured in this run by rced_ffma_peak (independent FFMA chains, 64 warps/SM); "
-                                    "MEASURED_PEAKS.json holds no FP32 figure; nominal 2*128*148*1.965 GHz = 74.4",
-                     "flops_per_launch": flops_valid, "flop_basis": "valid-tap MACs x2 (3,959,092 MAC/frame)",
-                     "kernel_ms": k2_ms, "kernel_share_of_step": k2_ms * args.steps / ms_total,
-                     "traffic": traffic},
+        "roofline": roofline(args.variant, achieved, ffma_peak, flops_valid, k2_ms, k2_ms * args.steps / ms_total, traffic,
+                             rows, tc_status),
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:

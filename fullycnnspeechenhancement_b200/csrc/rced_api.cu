@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -207,8 +208,15 @@ struct rced_handle {
     std::vector<float> folded;
     unsigned char* d_tc_img;
     float* d_tc_bias;
-    float* d_tc_skip;
-    unsigned int* d_tc_flags;
+    // The tensor-core kernel parks skip tensors in a per-CTA global scratch and reports through a
+    // flag word; launches on different streams may overlap, so each stream gets its own pair
+    // (allocated on the stream's first launch).
+    struct TcStream {
+        float* skip;
+        unsigned int* flags;
+    };
+    std::map<void*, TcStream> tc_streams;
+    unsigned int* last_tc_flags;
 };
 
 struct DeviceGuard {
@@ -312,8 +320,7 @@ int rced_create(int arch, const float* folded, size_t n_folded, int device, rced
     h->folded.assign(folded, folded + n_folded);
     h->d_tc_img = nullptr;
     h->d_tc_bias = nullptr;
-    h->d_tc_skip = nullptr;
-    h->d_tc_flags = nullptr;
+    h->last_tc_flags = nullptr;
     if ((e = cudaMalloc(&h->d_packed, packed.size() * sizeof(float))) != cudaSuccess) {
         delete h;
         return cuda_fail(e, "cudaMalloc(weights)");
@@ -334,8 +341,10 @@ void rced_destroy(rced_handle* h) {
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_tc_img) cudaFree(h->d_tc_img);
     if (h->d_tc_bias) cudaFree(h->d_tc_bias);
-    if (h->d_tc_skip) cudaFree(h->d_tc_skip);
-    if (h->d_tc_flags) cudaFree(h->d_tc_flags);
+    for (auto& kv : h->tc_streams) {
+        cudaFree(kv.second.skip);
+        cudaFree(kv.second.flags);
+    }
     delete h;
 }
 
@@ -412,17 +421,12 @@ int rced_set_variant(rced_handle* h, int variant) {
         std::vector<unsigned char> img((size_t)tc_image_bytes(h->arch));
         std::vector<float> bias((size_t)tc_bias_floats(h->arch));
         tc_pack_weights(h->arch, h->folded.data(), img.data(), bias.data());
-        const size_t skip_bytes = (size_t)h->num_sms * tc_skip_floats_per_cta(h->arch) * sizeof(float);
         cudaError_t e;
         if ((e = cudaMalloc(&h->d_tc_img, img.size())) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc image)");
         if ((e = cudaMalloc(&h->d_tc_bias, bias.size() * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc bias)");
-        if ((e = cudaMalloc(&h->d_tc_skip, skip_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc skip scratch)");
-        if ((e = cudaMalloc(&h->d_tc_flags, 2 * sizeof(unsigned int))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc flags)");
         if ((e = cudaMemcpy(h->d_tc_img, img.data(), img.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tc image)");
         if ((e = cudaMemcpy(h->d_tc_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
             return cuda_fail(e, "cudaMemcpy(tc bias)");
-        if ((e = cudaMemset(h->d_tc_skip, 0, skip_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMemset(tc skip scratch)");
-        if ((e = cudaMemset(h->d_tc_flags, 0, 2 * sizeof(unsigned int))) != cudaSuccess) return cuda_fail(e, "cudaMemset(tc flags)");
     }
     h->variant = variant;
     return RCED_OK;
@@ -430,10 +434,10 @@ int rced_set_variant(rced_handle* h, int variant) {
 int rced_variant(const rced_handle* h) { return h ? h->variant : -1; }
 int rced_tc_status(rced_handle* h, float* max_abs, unsigned int* protocol_error) {
     if (!h) return fail(RCED_ERR_ARG, "null handle");
-    if (!h->d_tc_flags) return fail(RCED_ERR_STATE, "tensor-core variant was never selected");
+    if (!h->last_tc_flags) return fail(RCED_ERR_STATE, "the tensor-core kernel has not been launched on this handle");
     DeviceGuard guard(h->device);
     unsigned int f[2];
-    cudaError_t e = cudaMemcpy(f, h->d_tc_flags, sizeof(f), cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(f, h->last_tc_flags, sizeof(f), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tc flags)");
     if (max_abs) memcpy(max_abs, &f[0], 4);
     if (protocol_error) *protocol_error = f[1];
@@ -482,14 +486,28 @@ int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n
         // tensor-core kernel first; the FP32 FFMA kernel follows on the same stream and returns at
         // once unless the range guard tripped (an activation beyond the FP16 range) or the
         // tensor-core kernel reported a protocol error -- stream-ordered, no host synchronisation
-        if ((e = cudaMemsetAsync(h->d_tc_flags, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream)) != cudaSuccess)
+        auto it = h->tc_streams.find(stream);
+        if (it == h->tc_streams.end()) {
+            rced_handle::TcStream ts{nullptr, nullptr};
+            const size_t skip_bytes = (size_t)h->num_sms * tc_skip_floats_per_cta(h->arch) * sizeof(float);
+            if ((e = cudaMalloc(&ts.skip, skip_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc skip scratch)");
+            if ((e = cudaMalloc(&ts.flags, 2 * sizeof(unsigned int))) != cudaSuccess) {
+                cudaFree(ts.skip);
+                return cuda_fail(e, "cudaMalloc(tc flags)");
+            }
+            it = h->tc_streams.emplace(stream, ts).first;
+        }
+        float* const d_skip = it->second.skip;
+        unsigned int* const d_flags = it->second.flags;
+        h->last_tc_flags = d_flags;
+        if ((e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream)) != cudaSuccess)
             return cuda_fail(e, "cudaMemsetAsync(tc flags)");
         // development aid: RCED_TC_TRACE=<file> dumps clock64 stamps of CTA 0's second batch (synchronises)
         const char* trace_path = getenv("RCED_TC_TRACE");
         long long* d_trace = nullptr;
         const int slots = tc_trace_slots(h->arch);
         if (trace_path && cudaMalloc(&d_trace, slots * sizeof(long long)) == cudaSuccess) cudaMemset(d_trace, 0, slots * sizeof(long long));
-        e = launch_net_tc(h->arch, p, h->d_tc_img, h->d_tc_bias, h->d_tc_skip, h->d_tc_flags, d_trace, h->num_sms, (cudaStream_t)stream);
+        e = launch_net_tc(h->arch, p, h->d_tc_img, h->d_tc_bias, d_skip, d_flags, d_trace, h->num_sms, (cudaStream_t)stream);
         count_launch();
         if (d_trace) {
             std::vector<long long> t(slots);
@@ -502,7 +520,7 @@ int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n
             cudaFree(d_trace);
         }
         if (e != cudaSuccess) return cuda_fail(e, "rced_forward launch (tensor-core variant)");
-        p.guard = h->d_tc_flags;
+        p.guard = d_flags;
     }
     e = launch_net(h->arch, h->skip_in_tmem, p, h->num_sms, (cudaStream_t)stream);
     count_launch();

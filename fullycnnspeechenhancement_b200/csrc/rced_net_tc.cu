@@ -318,29 +318,38 @@ __device__ __forceinline__ void epi_final_tile(const Ctx& c, const int pass, con
     const int fi = r / kFS, b = r - fi * kFS;
     const bool valid = fi < c.nf && b < kBins;
     const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
-    // tap = 48 pass + i stays inside the frame iff 0 <= b - tap + 64 <= 128
-    const int ilo = valid ? b - 64 - pass * kFinalTaps : 4096;
-    float am = 0.f, a0 = 0.f, ap = 0.f;
+    // tap = 48 pass + i stays inside the frame iff 0 <= b - tap + 64 <= 128: a contiguous range of
+    // i, kept as a bit mask so that the per-value test is one bit test
+    unsigned long long vmask = 0ull;
+    if (valid) {
+        const int ilo = b - 64 - pass * kFinalTaps, ihi = ilo + 128;
+        const int lo = ilo < 0 ? 0 : ilo, hi = ihi > kFinalTaps - 1 ? kFinalTaps - 1 : ihi;
+        if (lo <= hi) vmask = (~0ull >> (63 - hi)) & (~0ull << lo);
+    }
+    // running sums over the taps: s0 takes the values of diagonal m - 32 (i < lane), s1 those of
+    // m - 32 and m (i < lane + 32), tot everything; the three diagonals are differences of them
+    float s0 = 0.f, s1 = 0.f, tot = 0.f;
     float d[8];
     tmem_ld8(ta, d);
 #pragma unroll 1
     for (int g = 0; g < kFinalTaps / 8; ++g) {
         tmem_wait_ld();
         reg_fence8(d);
+        const uint32_t mb = (uint32_t)(vmask >> (8 * g));
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (unsigned)(g * 8 + e - ilo) <= 128u ? d[e] : 0.f;
+        for (int e = 0; e < 8; ++e) v[e] = (mb & (1u << e)) ? d[e] : 0.f;
         if (g + 1 < kFinalTaps / 8) tmem_ld8(ta + (g + 1) * 8, d);
+        const int base = g * 8 - c.lane;   // i - lane of e = 0; shfl takes the source lane modulo 32
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int i = g * 8 + e;
-            const float x = __shfl_sync(0xffffffffu, v[e], (i - c.lane) & 31);   // from lane l = (i - m) mod 32
-            const int q = (i - c.lane) >> 5;                                     // diagonal d = m + 32 q, q in {-1, 0, 1}
-            am += q < 0 ? x : 0.f;
-            a0 += q == 0 ? x : 0.f;
-            ap += q > 0 ? x : 0.f;
+            const float x = __shfl_sync(0xffffffffu, v[e], base + e);   // value of lane (i - m) mod 32
+            tot += x;
+            if (base + e < 32) s1 += x;
+            if (base + e < 0) s0 += x;
         }
     }
+    const float am = s0, a0 = s1 - s0, ap = tot - s1;
     // output row of diagonal d: r0 + 64 - 48 pass - d
     float* pw = c.priv;
     const int ro = r0 + 64 - pass * kFinalTaps - c.lane;
@@ -413,7 +422,10 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         e.pad0 = e.pad1 = 0;
         s_epi[li] = e;
     }
-    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kFlagSlot) = 0u;
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kFlagSlot) = 0u;
+        *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kNextInSlot) = 0u;
+    }
     for (int s = 0; s < NS; ++s) {
         const int nu = step_units(ARCH, s), nc = step_chunks(ARCH, s), ub = unit_base(ARCH, s);
         for (int u = threadIdx.x; u < nu; u += kThreads) {
@@ -526,6 +538,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         __syncwarp();
     } else if (warp == 1) {
         // ================= weight producer =================
+        // streams every step's weight tiles from L2 into the double buffer, two steps ahead
         uint32_t it = 0;
         for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
 #pragma unroll 1
@@ -543,6 +556,43 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 }
                 __syncwarp();
             }
+        }
+    } else if (warp == 4) {
+        // ================= input prefetch =================
+        // While a batch runs, fetches what the NEXT one needs at its start: the utterance bounds
+        // of its frames (a binary search over row_off: ten dependent L2 round trips) and its
+        // kFB + 7 input rows, into the half of the double buffer the batch before last used.
+        float* inbuf = reinterpret_cast<float*>(smem + smem_in_off(ARCH));
+        const uint32_t flag = bars + 8 * kFlagSlot;
+        uint32_t itn = 0;   // local index of the batch being prefetched
+        for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++itn) {
+            if (itn >= 2) {
+                // buffer itn & 1 was read by the staging of batch itn - 2: wait until the scout has
+                // seen that batch's input barrier (its counter has then passed the batch's first tile)
+                const uint32_t need = (itn - 2) * NS * kTiles + 1;
+                for (int spin = 0; ld_acquire(flag) < need; ++spin) {
+                    __nanosleep(200);
+                    if ((spin & 255) == 255 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
+                }
+            }
+            const long long g0 = batch * kFB;
+            long long* bn = bnd + (itn & 1) * 2 * kFB;
+            if (lane < kFB) {
+                long long lo = 0, hi = 0;
+                if (g0 + lane < p.total_rows) locate(p.row_off, p.n_utt, g0 + lane, lo, hi);
+                bn[2 * lane] = lo;
+                bn[2 * lane + 1] = hi;
+            }
+            float* ib = inbuf + (itn & 1) * kInRows * kInStride;
+            for (int j = 0; j < kInRows; ++j) {
+                const long long src = g0 - 3 + j;
+                const bool ok = src >= 0 && src < p.total_rows;
+                for (int b = lane; b < kBins; b += 32) ib[j * kInStride + b] = ok ? __ldg(p.in + src * kBins + b) : 0.f;
+            }
+            __syncwarp();
+            // a counter, not an mbarrier: this warp may be two batches ahead of the epilogue warps,
+            // which a phase parity could not tell apart
+            if (lane == 0) st_release(bars + 8 * kNextInSlot, itn + 1);
         }
     } else if (warp == 2) {
         // ================= dependency scout =================
@@ -599,13 +649,12 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             c.nf = left < kFB ? (int)left : kFB;
             c.g0 = g0;
             c.tracing = p.trace != nullptr && blockIdx.x == 0 && it == 1;
-            if (c.et < kFB) {
-                long long lo = 0, hi = 0;
-                if (c.et < c.nf) locate(p.row_off, p.n_utt, g0 + c.et, lo, hi);
-                bnd[2 * c.et] = lo;
-                bnd[2 * c.et + 1] = hi;
-            }
-            epi_bar();   // bounds visible; every MMA of the previous batch has completed (its epilogues waited)
+            // bounds and input rows of this batch were prefetched by the producer warp
+            for (int spin = 0; ld_acquire(bars + 8 * kNextInSlot) <= it; ++spin)
+                if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
+            const long long* bn = bnd + (it & 1) * 2 * kFB;
+            const float* ib = reinterpret_cast<const float*>(smem + smem_in_off(ARCH)) + (it & 1) * kInRows * kInStride;
+            epi_bar();   // every MMA of the previous batch has completed (its epilogues waited)
             // the output layer's accumulators of the previous batch overlaid planes 2 and 3 (hi),
             // halo rows included: those must read as zero again before any tap touches them
             if (it > 0 && c.et < 4 * 16) {
@@ -619,12 +668,12 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 const int fi = r / kFS, b = r - fi * kFS;
                 float v[8];
                 if (fi < c.nf && b < kBins) {
-                    const long long lo = bnd[2 * fi], hi = bnd[2 * fi + 1];
+                    const long long lo = bn[2 * fi], hi = bn[2 * fi + 1];
                     const long long g = g0 + fi;
 #pragma unroll
                     for (int tt = 0; tt < 8; ++tt) {
-                        const long long src = g + tt - 3;
-                        v[tt] = (src >= lo && src < hi) ? __ldg(p.in + src * kBins + b) : 0.f;
+                        const long long src = g + tt - 3;   // input row fi + tt of the prefetched block
+                        v[tt] = (src >= lo && src < hi) ? ib[(fi + tt) * kInStride + b] : 0.f;
                         amax = fmaxf(amax, fabsf(v[tt]));
                     }
                 } else {

@@ -29,11 +29,14 @@ constexpr int kActBytes = 2 * kPlanes * kPlane16 * 16;
 constexpr int kAccCols = 64;                  // tensor-memory columns per tile
 constexpr int kFinalTaps = 48;                // taps of the (1,129) layer per pass (N of the pass)
 constexpr int kFinalPasses = 3;
-constexpr int kCtrlWarps = 4;                 // warps 0 / 3: MMA issue of the even / odd row tiles, 1: weight producer, 2: dependency scout
+constexpr int kCtrlWarps = 5;                 // warps 0 / 3: MMA issue of the even / odd row tiles, 1: weight producer, 2: dependency scout,
+                                              // 4: prefetch of the next batch's utterance bounds and input rows
 constexpr int kEpiWarps = 16;                 // groups of four warps (one per tensor-memory lane quadrant)
 constexpr int kGroups = kEpiWarps / 4;        // group g takes the row tiles t = g, g + kGroups, ...
 constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
 constexpr int kTraceEvents = 8;               // clock stamps per (step, tile) of the development trace
+constexpr int kInRows = kFB + 7;              // input rows a batch reads: frames g0-3 .. g0+kFB+3
+constexpr int kInStride = 132;                // floats per prefetched input row
 constexpr int kOutStride = 132;               // floats per frame of the output accumulator
 
 static_assert(kFB * kFS <= kRows, "frames of a batch must fit the row tiles");
@@ -113,10 +116,11 @@ RCED_HD constexpr int smem_tab_off(int arch) { return smem_w_off(arch, 2); }    
 RCED_HD constexpr int smem_step_off(int arch) { return smem_tab_off(arch) + pad128(8 * total_units(arch)); }   // int4[n_steps]
 RCED_HD constexpr int smem_bias_off(int arch) { return smem_step_off(arch) + pad128(16 * n_steps(arch)); }     // float[n_steps][32]
 RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 128 * n_steps(arch); }             // float[kFB][kOutStride]
-RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + pad128(4 * kFB * kOutStride); }     // long long[kFB][2]
-RCED_HD constexpr int smem_bar_off(int arch) { return smem_bnd_off(arch) + 128; }                              // mbarriers
+RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + pad128(4 * kFB * kOutStride); }     // long long[2][kFB][2]
+RCED_HD constexpr int smem_bar_off(int arch) { return smem_bnd_off(arch) + 256; }                              // mbarriers
 RCED_HD constexpr int smem_epi_off(int arch) { return smem_bar_off(arch) + 256; }                             // EpiStep[n_steps]
-RCED_HD constexpr int smem_total(int arch) { return smem_epi_off(arch) + 32 * n_steps(arch); }
+RCED_HD constexpr int smem_in_off(int arch) { return smem_epi_off(arch) + pad128(32 * n_steps(arch)); }       // float[2][kInRows][kInStride]
+RCED_HD constexpr int smem_total(int arch) { return smem_in_off(arch) + 2 * kInRows * kInStride * 4; }
 
 // mbarrier slots (8 bytes each) inside the barrier block
 constexpr int kBarAccFull = 0;     // [kTiles]  tcgen05.commit after the last MMA of (step, tile)
@@ -125,6 +129,7 @@ constexpr int kBarWFull = 16;      // [2]       weights of a step landed in buff
 constexpr int kBarWFree = 18;      // [2]       MMAs reading buffer b complete
 constexpr int kBarInReady = 20;    //           layer-0 input of the batch staged
 constexpr int kBarConvDone = 21;   //           every MMA of the batch's last conv layer complete
+constexpr int kNextInSlot = 25;    //           u32 count of batches whose bounds / input rows the producer has prefetched
 constexpr int kFlagSlot = 24;      //           u32 progress counter published by the dependency scout
 
 }  // namespace tc

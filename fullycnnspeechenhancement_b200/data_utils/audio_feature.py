@@ -29,7 +29,7 @@ class AudioFeature(object):
         if self._eng is None:
             from ..engine import Enhancer
             n = _lib.lib().rced_folded_weight_count(2)
-            self._eng = Enhancer("FullyCNNV2", np.zeros(n, np.float32), device=self.device_index)
+            self._eng = Enhancer("FullyCNNV2", np.zeros(n, np.float32), device=self.device_index, variant="ffma")
         return self._eng
 
     def compute_spectrogram(self, signal, sample_rate, window_s=0.02, stride_s=0.01, nfft=512, use_complex=False):

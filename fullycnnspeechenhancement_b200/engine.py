@@ -56,10 +56,14 @@ def _ptr(t):
 
 
 class Enhancer(object):
-    def __init__(self, net_work, weights, device=0, irfft_n=512):
+    def __init__(self, net_work, weights, device=0, irfft_n=512, variant="tc"):
         """``weights``: dict of TensorFlow-named variables (see model_utils/fold.py) or an
         already folded flat float32 vector.  ``irfft_n``: 512 is what the reference ships
-        (model_utils/utils.py:94), 256 is the mathematically consistent inverse."""
+        (model_utils/utils.py:94), 256 is the mathematically consistent inverse.
+        ``variant``: network kernel, "tc" (tcgen05 tensor cores with the FP16 x3 split, the FP32 FFMA
+        kernel behind it as range-guard fall-back; default) or "ffma" (FP32 FFMA kernel only).  "tc" is
+        refused by the library when a folded weight exceeds the FP16 range; the engine then stays on
+        "ffma" (``self.variant`` tells which kernel runs)."""
         if not torch.cuda.is_available():
             raise _lib.RcedError("no CUDA device: the enhancement path has no CPU fallback")
         self.lib = _lib.lib()
@@ -79,6 +83,14 @@ class Enhancer(object):
         self._h = h
         self._streams = None
         self._ws = {}
+        self.variant = "ffma"
+        if variant == "tc":
+            try:
+                self.set_variant("tc")
+            except _lib.RcedError:
+                pass
+        elif variant != "ffma":
+            raise ValueError("variant must be 'tc' or 'ffma'")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -99,6 +111,7 @@ class Enhancer(object):
         FFMA kernel as stream-ordered fall-back when an activation leaves the FP16 range)."""
         v = {"ffma": _lib.VARIANT_FFMA, "tc": _lib.VARIANT_TC}.get(variant, variant)
         _lib.check(self.lib.rced_set_variant(self._h, int(v)))
+        self.variant = "tc" if int(v) == _lib.VARIANT_TC else "ffma"
 
     def tc_status(self):
         """(largest |activation| stored as FP16, protocol error code) of the last tensor-core launch."""

@@ -70,7 +70,7 @@ class AudioReBuild(object):
             from .. import _lib
             from ..engine import Enhancer
             n = _lib.lib().rced_folded_weight_count(2)
-            self._eng = Enhancer("FullyCNNV2", np.zeros(n, np.float32), device=self.device_index)
+            self._eng = Enhancer("FullyCNNV2", np.zeros(n, np.float32), device=self.device_index, variant="ffma")
         return self._eng
 
     def rebuild_audio(self, sig_length_list, spec, phase, sample_rate, windows_ms, stride_ms):

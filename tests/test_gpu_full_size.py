@@ -46,10 +46,21 @@ def test_config0_v1_single_utterance(pool):
     assert rebuild.sdr_db(oracle_chain(arch, w, pool[0]), out) >= SNR_DB
 
 
-def test_config1_v2_1024_utterances(pool):
+def same_result(a, b, variant):
+    """The FP32 FFMA kernel computes every frame with the same instruction sequence wherever it sits in
+    a batch: results are bit-identical.  In the tensor-core kernel the summation order of the output
+    layer depends on the frame's row position inside the 7-frame batch: identical up to FP32 rounding
+    (>= 100 dB; measured ~120 dB)."""
+    if variant == "ffma":
+        return np.array_equal(a, b)
+    return rebuild.sdr_db(a, b) >= 100.0
+
+
+@pytest.mark.parametrize("variant", ["tc", "ffma"])
+def test_config1_v2_1024_utterances(pool, variant):
     arch = "FullyCNNV2"
     w = network.random_weights(arch, seed=11, randomize_bn=True)
-    eng = Enhancer(arch, w, device=0)
+    eng = Enhancer(arch, w, device=0, variant=variant)
     n = 1024
     waves = [pool[i % len(pool)] for i in range(n)]
     outs = eng.enhance(waves, chunk_utts=256)
@@ -57,18 +68,19 @@ def test_config1_v2_1024_utterances(pool):
     assert all(np.isfinite(o).all() for o in outs[::37])
     # determinism / batch independence: the same waveform gives the same bits wherever it sits in the batch
     for i in range(len(pool), n, 53):
-        assert np.array_equal(outs[i], outs[i % len(pool)]), i
+        assert same_result(outs[i], outs[i % len(pool)], variant), i
     alone = eng.enhance([pool[3]])[0]
-    assert np.array_equal(alone, outs[3])
+    assert same_result(alone, outs[3], variant)
     for i in (0, 5, 15):
         assert rebuild.sdr_db(oracle_chain(arch, w, pool[i]), outs[i]) >= SNR_DB
     eng.close()
 
 
-def test_config2_v3_4096_ragged():
+@pytest.mark.parametrize("variant", ["tc", "ffma"])
+def test_config2_v3_4096_ragged(variant):
     arch = "FullyCNNV3"
     w = network.random_weights(arch, seed=12, randomize_bn=True)
-    eng = Enhancer(arch, w, device=0)
+    eng = Enhancer(arch, w, device=0, variant=variant)
     rng = np.random.default_rng(2)
     n = 4096
     lengths = rng.integers(16000, 64001, n)                      # 2-8 s, voicebank-shaped
@@ -79,16 +91,17 @@ def test_config2_v3_4096_ragged():
     # chunking must not matter, and neither must the batch mates
     again = eng.enhance(waves[100:140], chunk_utts=7)
     for a, b in zip(again, outs[100:140]):
-        assert np.array_equal(a, b)
+        assert same_result(a, b, variant)
     for i in (0, 1234, 4095):
         assert rebuild.sdr_db(oracle_chain(arch, w, waves[i]), outs[i]) >= SNR_DB
     eng.close()
 
 
-def test_config3_one_hour_stream():
+@pytest.mark.parametrize("variant", ["tc", "ffma"])
+def test_config3_one_hour_stream(variant):
     arch = "FullyCNNV2"
     w = network.random_weights(arch, seed=13, randomize_bn=True)
-    eng = Enhancer(arch, w, device=0)
+    eng = Enhancer(arch, w, device=0, variant=variant)
     L = 8000 * 3600
     minute = noisy_utterance(9000, 8000 * 60)
     # an hour made of a repeated minute with a slow gain drift, so that no two chunks are equal

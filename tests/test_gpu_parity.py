@@ -36,7 +36,7 @@ def engines():
     out = {}
     for a in ARCHS:
         w = network.random_weights(a, seed=1234, randomize_bn=True)
-        out[a] = (Enhancer(a, w, device=0), w)
+        out[a] = (Enhancer(a, w, device=0, variant="ffma"), w)   # the FP32 FFMA kernel; tests/test_gpu_tc.py covers "tc"
     yield out
     for e, _ in out.values():
         e.close()

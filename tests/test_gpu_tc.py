@@ -37,13 +37,14 @@ def engines():
 
 def _forward(eng, mag, row_off, variant):
     dev = eng.device
+    assert eng.variant == "tc"      # the engine's default
     eng.set_variant(variant)
     d_mag = torch.from_numpy(np.ascontiguousarray(mag, np.float32)).to(dev)
     d_ro = torch.from_numpy(np.asarray(row_off, np.int64)).to(dev)
     pred = eng.forward_device(d_mag, d_ro)
     torch.cuda.synchronize()
     out = pred.cpu().numpy()
-    eng.set_variant("ffma")
+    eng.set_variant("tc")
     return out
 
 
@@ -109,12 +110,8 @@ def test_tc_range_guard_falls_back_to_ffma(engines):
 def test_tc_end_to_end_waveforms(engines):
     eng, w = engines["FullyCNNV2"]
     waves = [noisy_utterance(7, 8000), noisy_utterance(8, 4321), noisy_utterance(9, 32000)]
-    eng.set_variant("tc")
-    try:
-        outs = eng.enhance(waves)
-    finally:
-        eng.set_variant("ffma")
-    assert eng.tc_status()[1] == 0
+    outs = eng.enhance(waves)       # default variant: tc
+    assert eng.variant == "tc" and eng.tc_status()[1] == 0
     for wv, o in zip(waves, outs):
         X = stft.compute_spectrogram(wv, 8000, 0.032, 0.016, 256, True).T[None, :, :, None]
         mag = stft.power_spectrum(X).astype(np.float32)
@@ -122,3 +119,26 @@ def test_tc_end_to_end_waveforms(engines):
         ref = rebuild.rebuild_audio([len(wv)], pred[..., 0], stft.divide_phase(X)[..., 0], 8000, 32.0, 16.0)[0]
         assert len(o) == len(wv)
         assert rebuild.sdr_db(ref, o) >= 60.0
+
+
+def test_tc_concurrent_streams_do_not_share_scratch(engines):
+    """Launches on different streams may overlap on the GPU: each stream owns its skip scratch and
+    guard flags (a shared scratch corrupted the last batches of a launch, found by the streaming test)."""
+    eng, _ = engines["FullyCNNV2"]
+    dev = eng.device
+    rng = np.random.default_rng(31)
+    rows = 148 * 7 * 4 + 5
+    ro = torch.tensor([0, rows], dtype=torch.int64, device=dev)
+    mags = [torch.from_numpy(np.abs(rng.normal(0, 2, (rows, 129))).astype(np.float32)).to(dev) for _ in range(3)]
+    ref = [eng.forward_device(m, ro).clone() for m in mags]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+    outs = [torch.empty_like(m) for m in mags]
+    for _ in range(3):
+        for s, m, o in zip(streams, mags, outs):
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                eng.forward_device(m, ro, pred=o, stream=s)
+    torch.cuda.synchronize()
+    for o, r in zip(outs, ref):
+        assert torch.equal(o, r)
