@@ -91,6 +91,17 @@ __device__ __forceinline__ uint32_t ld_acquire(uint32_t addr) {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+// Both barriers complete: the two tests of a round are in flight together, so the wake-up costs one
+// test latency (~160 cycles) after the later arrival instead of two.
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t bar_b, uint32_t parity, unsigned int* err, int code) {
+    for (int it = 0; it < (1 << 22); ++it) {
+        const bool a = mbar_test(bar_a, parity);
+        const bool b = mbar_test(bar_b, parity);
+        if (a && b) return;
+        if ((it & 255) == 255 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) return;
+    }
+    atomicMax(err, (unsigned int)code);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -253,8 +264,7 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
     // accumulator is complete with acc_full[t]; the neighbour tile's commit (other thread) also
     // covers that thread's earlier tile on the other side -- so nobody reads this tile's rows as
     // a halo any more and the planes can be updated in place
-    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 100 + s);
-    mbar_wait(bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t - 1)), par, c.err, 200 + s);
+    mbar_wait2(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t - 1)), par, c.err, 100 + s);
     fence_after();
     stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 2);
 
@@ -431,7 +441,12 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         for (int u = threadIdx.x; u < nu; u += kThreads) {
             const int o0 = chunk_off16(ARCH, s, 2 * u);
             const int o1 = 2 * u + 1 < nc ? chunk_off16(ARCH, s, 2 * u + 1) : o0 + 1;   // dummy chunk: zero weights
-            tab[ub + u] = make_int2(o0, o1 - o0);
+            // the finished low words of the unit's A (row tile 0, hi planes) and B descriptors: steps
+            // alternate between the two weight buffers and n_steps is even, so step s always uses buffer s & 1
+            const uint32_t a16 = (smem_u32(act) >> 4) + kLead + (uint32_t)o0;
+            const uint32_t w16 = (smem_u32(smem + smem_w_off(ARCH, s & 1)) >> 4) + (uint32_t)(u * (step_tile_bytes(ARCH, s) >> 4));
+            tab[ub + u] = make_int2((int)((a16 & 0x3FFFu) | ((uint32_t)(o1 - o0) << 16)),
+                                    (int)((w16 & 0x3FFFu) | ((uint32_t)step_tile_rows(ARCH, s) << 16)));
         }
         if (threadIdx.x == 0)
             steps[s] = make_int4(nu, ub, step_np(ARCH, s), (step_tile_bytes(ARCH, s) >> 4) | (is_final(ARCH, s) ? (1 << 16) : 0));
@@ -470,7 +485,6 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         // registers (fully unrolled, kMaxUnits slots): issuing a unit is an add and the MMA pair.
         const int t_first = warp == 0 ? 0 : 1;
         if (elect_one()) {
-            const uint32_t act16 = smem_u32(act) >> 4;
             const uint32_t flag = bars + 8 * kFlagSlot;
             uint32_t seen = 0;   // last value read from the scout's counter
             uint32_t it = 0;
@@ -481,19 +495,15 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                     const uint32_t k = it * NS + s;
                     const int wb = k & 1;
                     const int4 st = steps[s];
-                    const int nu = st.x, np = st.z, tile16 = st.w & 0xFFFF;
+                    const int nu = st.x, np = st.z;
                     const bool fin = (st.w >> 16) != 0;
                     const int2* ut = tab + st.y;
-                    const uint32_t w16 = smem_u32(smem + smem_w_off(ARCH, wb)) >> 4;
                     const uint32_t id_a = idesc_f16(fin ? np : 2 * np), id_b = idesc_f16(np);
-                    const uint32_t b_lbo = (uint32_t)(2 * np) << 16;   // LBO of the B tile: rows per chunk x 16 bytes
-                    uint32_t ua[kMaxUnits], ub[kMaxUnits];
+                    uint32_t ua[kMaxUnits];   // A descriptor low words, built at kernel start
 #pragma unroll
-                    for (int u = 0; u < kMaxUnits; ++u) {
-                        const int2 e = ut[u < nu ? u : 0];
-                        ua[u] = ((act16 + kLead + (uint32_t)e.x) & 0x3FFFu) | ((uint32_t)e.y << 16);
-                        ub[u] = ((w16 + (uint32_t)(u * tile16)) & 0x3FFFu) | b_lbo;
-                    }
+                    for (int u = 0; u < kMaxUnits; ++u) ua[u] = (uint32_t)ut[u < nu ? u : 0].x;
+                    const uint32_t ub0 = (uint32_t)ut[0].y;             // B descriptor of unit 0; unit u is tile16 * u further
+                    const uint32_t tile16 = (uint32_t)(st.w & 0xFFFF);
 #pragma unroll 1
                     for (int t = t_first; t < kTiles; t += 2) {
                         // the scout (warp 2) has waited on this tile's mbarriers and published its index: a
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
 #pragma unroll
                             for (int u = 0; u < kMaxUnits; ++u) {
                                 if (u < nu) {
-                                    const uint64_t db = make_desc(ub[u]);
+                                    const uint64_t db = make_desc(ub0 + (uint32_t)u * tile16);
                                     umma_f16(d, make_desc(ua[u] + toff), db, id_a, u > 0);     // hi x [Whi | Wlo] -> columns [0, 2 NP)
                                     umma_f16(d, make_desc(ua[u] + toff + kLo16), db, id_b, 1); // lo x Whi        -> columns [0, NP)
                                     if (u == 0) stamp(p.trace, tr, s, t, 6);
@@ -521,10 +531,10 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                             }
                         } else {
                             // output layer pass: one unit; hi x Whi, lo x Whi, hi x Wlo (rows 48..95 of the tile)
-                            const uint64_t db = make_desc(ub[0]);
+                            const uint64_t db = make_desc(ub0);
                             umma_f16(d, make_desc(ua[0] + toff), db, id_a, 0);
                             umma_f16(d, make_desc(ua[0] + toff + kLo16), db, id_a, 1);
-                            umma_f16(d, make_desc(ua[0] + toff), make_desc(ub[0] + (uint32_t)np), id_a, 1);
+                            umma_f16(d, make_desc(ua[0] + toff), make_desc(ub0 + (uint32_t)np), id_a, 1);
                         }
                         stamp(p.trace, tr, s, t, 7);
                         umma_commit(bars + 8 * (kBarAccFull + t));

@@ -85,6 +85,7 @@ RCED_HD constexpr int max_units(int arch) {
     return m;
 }
 constexpr int kMaxUnits = 18;   // register slots of the MMA issue loop
+static_assert(n_steps(1) % 2 == 0 && n_steps(2) % 2 == 0 && n_steps(3) % 2 == 0, "step s must always use weight buffer s & 1");
 static_assert(max_units(1) <= kMaxUnits && max_units(2) <= kMaxUnits && max_units(3) <= kMaxUnits, "raise kMaxUnits");
 
 // A-operand addressing of chunk c of step s, in 16-byte units relative to row (kLead + 128 t)
