@@ -1,12 +1,15 @@
-"""AudioParser / DataSet / DataLoader with the reference's interface
+"""AudioParser / DataSet / Sampler / DataLoader with the reference's interface
 (data_utils/data_loader.py of the reference), feeding the CUDA path.
 
 The hot-path pieces are AudioParser.parse_audio (STFT kernel) and the batch layout contract of
 DataLoader.padding_batch: zero-pad every [F, T_i] spectrogram to T_max and return
-[N, T_max, F, 1] (data_loader.py:198-209).  Manifest handling and noise mixing follow the
-reference's formulas; file decoding uses scipy (audio_io.py) because librosa is not available."""
+[N, T_max, F, 1] (data_loader.py:198-209).  Manifest handling, clean/noise pairing, noise mixing
+and batch binning follow the reference's behaviour; file decoding uses scipy (audio_io.py)
+because librosa is not available, and items are fetched by a thread pool (``num_works``) where
+the reference forks joblib workers (the per-item work here is file decoding plus a CUDA call)."""
 import codecs
 import json
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -27,11 +30,14 @@ class AudioParser(object):
         return audio_io.load_wav(audio_filepath, self.sample_rate)
 
     def add_noise(self, speech, noise):
-        """Mix at self.snr dB (data_loader.py:35-52): tile / crop the noise to the speech length,
-        scale it so that sum(speech^2)/sum(noise^2) == 10^(snr/10)."""
+        """Mix at self.snr dB (data_loader.py:35-52).  A noise clip shorter than the speech is
+        extended by doubling (each appended copy of the whole clip-so-far scaled by one
+        uniform(0, 2) draw), a longer one is cropped at a random start; then it is scaled so that
+        sum(speech^2) / sum(noise^2) == 10^(snr/10).  Draws come from numpy's global generator in
+        the reference's order, so a seeded run mixes identically."""
         if len(speech) >= len(noise):
-            reps = int(np.ceil((len(speech) - len(noise)) / len(noise)))
-            for _ in range(reps):
+            rounds = int(np.ceil((len(speech) - len(noise)) / len(noise)))
+            for _ in range(rounds):
                 noise = np.concatenate((noise, noise * np.random.uniform(0, 2)))
             noise = noise[:len(speech)]
         else:
@@ -47,58 +53,140 @@ class AudioParser(object):
 
 
 class DataSet(AudioParser):
-    """JSON-lines manifest reader (data_loader.py:64-125): items need ``audio_filepath`` and
-    ``duration``; items outside [min_duration, max_duration] are dropped."""
+    """JSON-lines manifests (data_loader.py:64-125).  Every line needs ``duration``; lines outside
+    [min_duration, max_duration] are dropped.  With a noise manifest, item i is
+    ``audio_filepath`` of the speech manifest mixed with ``audio_filepath`` of noise item i (the
+    noise list is repeated until it is at least as long); without one, every line names a
+    ``clean_audio_filepath`` / ``mix_audio_filepath`` pair."""
 
     def __init__(self, manifest_filepath, noise_manifest, sample_rate=16000, window_ms=32, stride_ms=16, snr=0,
-                 min_duration=0.4, max_duration=float("inf"), use_complex=False):
-        super(DataSet, self).__init__(sample_rate, window_ms, stride_ms, snr, None, use_complex)
-        self.item_list = self._read_manifest(manifest_filepath, min_duration, max_duration)
-        self.noise_list = self._read_manifest(noise_manifest, 0.0, float("inf")) if noise_manifest else None
-        self.size = len(self.item_list)
+                 min_duration=0.4, max_duration=float("inf"), windows_name=None, use_complex=False):
+        super(DataSet, self).__init__(sample_rate=sample_rate, window_ms=window_ms, stride_ms=stride_ms, snr=snr,
+                                      windows_name=windows_name, use_complex=use_complex)
+        self.min_duration = min_duration
+        self.max_duration = max_duration
+        self.noise_manifest = noise_manifest
+        self.item_list = self.read_manifest(manifest_filepath)
+        if noise_manifest is not None:
+            self.noise_list = self.read_manifest(noise_manifest)
+            if len(self.noise_list) < len(self.item_list):
+                self.noise_list = self.noise_list * int(np.ceil(len(self.item_list) / len(self.noise_list)))
+            assert len(self.noise_list) >= len(self.item_list)
 
-    @staticmethod
-    def _read_manifest(path, min_duration, max_duration):
-        items = []
-        with codecs.open(path, "r", "utf-8") as f:
+    def read_manifest(self, manifest_path):
+        manifest = []
+        with codecs.open(manifest_path, "r", "utf-8") as f:
             for line in f:
-                line = line.strip()
-                if not line:
-                    continue
-                item = json.loads(line)
-                if min_duration <= float(item.get("duration", min_duration)) <= max_duration:
-                    items.append(item)
-        return items
+                try:
+                    item = json.loads(line)
+                except Exception as e:
+                    raise IOError("Error reading manifest: %s" % str(e))
+                if self.max_duration >= item["duration"] >= self.min_duration:
+                    manifest.append(item)
+        return manifest
 
-    def __len__(self):
-        return self.size
+    def item_name(self, index):
+        """File the outputs of item ``index`` are named after.  The reference's tester always reads
+        ``audio_filepath`` (tester.py:148), which paired manifests do not have; here those fall
+        back to the clean file."""
+        item = self.item_list[index]
+        return item["audio_filepath"] if "audio_filepath" in item else item["clean_audio_filepath"]
+
+    def load_pair(self, index):
+        """(mix_sig, speech) of item ``index`` -- the waveform half of ``__getitem__``."""
+        item = self.item_list[index]
+        if self.noise_manifest is not None:
+            speech, _ = self.load_audio(item["audio_filepath"])
+            noise, _ = self.load_audio(self.noise_list[index]["audio_filepath"])
+            return self.add_noise(speech, noise), speech
+        speech, _ = self.load_audio(item["clean_audio_filepath"])
+        mix_sig, _ = self.load_audio(item["mix_audio_filepath"])
+        return mix_sig, speech
 
     def __getitem__(self, index):
-        """((mix_sig, clean_sig), (mix_spec, clean_spec)) like the reference's item tuple."""
-        item = self.item_list[index]
-        clean, _ = self.load_audio(item.get("audio_filepath", item.get("clean_filepath")))
-        if self.noise_list:
-            noise_item = self.noise_list[np.random.randint(0, len(self.noise_list))]
-            noise, _ = self.load_audio(noise_item["audio_filepath"])
-            mix = self.add_noise(clean, noise).astype(np.float32)
-        elif "noisy_filepath" in item:
-            mix, _ = self.load_audio(item["noisy_filepath"])
-        else:
-            mix = clean
-        return (mix, clean), (self.parse_audio(mix), self.parse_audio(clean))
+        """((mix_sig, speech), (mix_spec, speech_spec)), the reference's item tuple."""
+        mix_sig, speech = self.load_pair(index)
+        speech_spec = self.parse_audio(speech)
+        mix_spec = self.parse_audio(mix_sig)
+        return (mix_sig, speech), (mix_spec, speech_spec)
+
+    def __len__(self):
+        return len(self.item_list)
+
+    def __call__(self, *args, **kwargs):
+        return self
 
     def shuffle(self):
         np.random.shuffle(self.item_list)
 
 
+class Sampler(object):
+    """Batch index bins in random order (data_loader.py:128-160).  ``drop_last`` cuts the ragged
+    tail off the dataset's item list; otherwise the list is EXTENDED with its last items up to the
+    next multiple of the batch size -- a whole extra batch when it already divides, as in the
+    reference (int(n / b) + 1 batches)."""
+
+    def __init__(self, dataset, batch_size, start_index=0, drop_last=False):
+        self.dataset = dataset
+        self.batch_size = batch_size
+        self.start_index = start_index
+        n = len(self.dataset)
+        if drop_last:
+            last_size = n % batch_size
+            # [:-0] would empty the list: the reference does exactly that when n divides evenly
+            self.dataset.item_list = self.dataset.item_list[:-last_size]
+        else:
+            last_size = (int(n / batch_size) + 1) * batch_size - n
+            self.dataset.item_list.extend(self.dataset.item_list[-last_size:])
+        ids = list(range(len(self.dataset)))
+        self.bins = [ids[i:i + self.batch_size] for i in range(0, len(ids), self.batch_size)]
+        self.indices = (np.random.permutation(len(self.bins) - self.start_index) + self.start_index).tolist()
+
+    def __iter__(self):
+        for x in self.indices:
+            batch_ids = self.bins[x]
+            np.random.shuffle(batch_ids)
+            yield batch_ids
+
+    def __len__(self):
+        return len(self.bins) - self.start_index
+
+    def reset_start_index(self, start_index):
+        self.start_index = start_index
+
+    def __call__(self, *args, **kwargs):
+        return self
+
+    def iter_num(self):
+        return len(self.indices)
+
+
 class DataLoader(object):
-    def __init__(self, dataset, batch_size, sampler=None, num_works=1):
+    def __init__(self, dataset, batch_size, sampler=None, num_works=2):
         self.dataset = dataset
         self.batch_size = batch_size
         self.sampler = sampler
         self.num_works = num_works
-        n = len(dataset)
-        self.bins = [list(range(i, min(i + batch_size, n))) for i in range(0, n, batch_size)]
+        self.q = []
+        if self.sampler is None:
+            n = len(self.dataset)
+            self.bins = [list(range(i, min(i + self.batch_size, n))) for i in range(0, n, self.batch_size)]
+
+    def one_point(self, x):
+        a, b = self.dataset[x]
+        return a, b
+
+    def pool_process(self, index_list):
+        """Fetch the items of one batch in order.  Items that draw random numbers (noise mixing)
+        are fetched serially so that a seeded run reproduces; pure file pairs go through a thread
+        pool of ``num_works``."""
+        serial = getattr(self.dataset, "noise_manifest", None) is not None or self.num_works is None or self.num_works <= 1
+        if serial:
+            results = [self.one_point(i) for i in index_list]
+        else:
+            with ThreadPoolExecutor(max_workers=int(self.num_works)) as pool:
+                results = list(pool.map(self.one_point, index_list))
+        self.q.extend(results)
 
     @staticmethod
     def padding_batch(batch_list):
@@ -118,9 +206,17 @@ class DataLoader(object):
         return mix, clean, mix_sig, clean_sig
 
     def __iter__(self):
-        groups = self.sampler if self.sampler is not None else self.bins
+        if self.sampler is not None:
+            if self.sampler.batch_size != self.batch_size:
+                self.batch_size = self.sampler.batch_size
+                print("Warrning: sampler.batch_size != batch_size. batch_size changed!")
+            groups = self.sampler
+        else:
+            groups = self.bins
         for index_list in groups:
-            yield self.collect_fn([self.dataset[i] for i in index_list])
+            self.pool_process(index_list)
+            results, self.q = self.q, []
+            yield self.collect_fn(results)
 
     def __len__(self):
         return len(self.sampler) if self.sampler is not None else len(self.bins)

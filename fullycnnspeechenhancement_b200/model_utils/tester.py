@@ -88,9 +88,8 @@ class FullyCNNTester(BaseTester):
             denoise = [np.asarray(d[:len(c)], dtype=np.float64) for d, c in zip(denoise, clean_sig)]
             for i in range(len(audio_bins)):
                 n = min(len(clean_sig[i]), len(denoise[i]))
-                self.sdr_score.update(sdr(clean_sig[i][:n], denoise[i][:n]))
-                item = valid_loader.dataset.item_list[audio_bins[i]]
-                name = os.path.basename(item.get("audio_filepath", item.get("clean_filepath", "utt_%d.wav" % audio_bins[i])))
+                self.sdr_score.update(sdr(np.asarray(clean_sig[i][:n]), denoise[i][:n]))
+                name = os.path.basename(valid_loader.dataset.item_name(audio_bins[i]))
                 audio_io.write_wav(os.path.join(self.audio_save_path, name), clean_sig[i], self.sample_rate)
                 audio_io.write_wav(os.path.join(self.audio_save_path, name.replace(".wav", "_mix.wav")), mix_sig[i], self.sample_rate)
                 audio_io.write_wav(os.path.join(self.audio_save_path, name.replace(".wav", "_de.wav")), denoise[i], self.sample_rate)

@@ -18,19 +18,20 @@ class AverageMeter(object):
 
     def update(self, val, n=1):
         self.val = val
-        self.sum += val * n
+        self.sum += val          # the reference adds val once whatever n is (utils.py:26-30)
         self.count += n
         self.avg = self.sum / self.count
 
 
 class SDR(object):
-    """10*log10(||ref||^2 / ||est - ref||^2) (utils.py:68-90 of the reference)."""
+    """10*log10(||y||^2 / (||y_pred - y||^2 + eps_f32)) (utils.py:64-90 of the reference)."""
 
-    def sdr(self, ref, est):
-        assert len(ref) == len(est)
-        ref = np.asarray(ref, dtype=np.float64)
-        est = np.asarray(est, dtype=np.float64)
-        return 10 * np.log10(np.sum(ref ** 2) / np.sum((est - ref) ** 2))
+    def sdr(self, y, y_pred):
+        assert len(y.shape) == 1
+        assert len(y) == len(y_pred)
+        y_en = np.power(y, 2).sum()
+        err_en = np.power(y_pred - y, 2).sum()
+        return 10 * np.log10(y_en / (err_en + np.finfo(np.float32).eps))
 
     def __call__(self, x, y):
         return self.sdr(x, y)

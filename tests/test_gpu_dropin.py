@@ -40,11 +40,25 @@ def workdir(tmp_path_factory):
         p = str(d / ("utt%d.wav" % i))
         audio_io.write_wav(p, noisy_utterance(70 + i, L), 8000)
         wavs.append(p)
+    # paired manifest (no noise manifest): the keys DataSet.__getitem__ reads at data_loader.py:113-118 of
+    # the reference, plus audio_filepath, which its tester uses to name the outputs (tester.py:148)
     manifest = str(d / "manifest.dev")
     with open(manifest, "w") as f:
         for p, L in zip(wavs, [16000, 12345, 8000]):
+            f.write(json.dumps({"audio_filepath": p, "clean_audio_filepath": p, "mix_audio_filepath": p,
+                                "duration": L / 8000.0}) + "\n")
+    # speech + noise manifests (mixing at snr dB inside the loader)
+    speech_manifest, noise_manifest = str(d / "manifest.speech"), str(d / "manifest.noise")
+    noise_wav = str(d / "noise0.wav")
+    audio_io.write_wav(noise_wav, 0.3 * np.random.default_rng(5).normal(size=5000).clip(-3, 3) / 3, 8000)
+    with open(speech_manifest, "w") as f:
+        for p, L in zip(wavs, [16000, 12345, 8000]):
             f.write(json.dumps({"audio_filepath": p, "duration": L / 8000.0}) + "\n")
-    return dict(dir=d, weights=w, prefix=prefix, wavs=wavs, manifest=manifest)
+        f.write(json.dumps({"audio_filepath": wavs[0], "duration": 0.1}) + "\n")        # below min_duration: dropped
+    with open(noise_manifest, "w") as f:
+        f.write(json.dumps({"audio_filepath": noise_wav, "duration": 5000 / 8000.0}) + "\n")
+    return dict(dir=d, weights=w, prefix=prefix, wavs=wavs, manifest=manifest, speech_manifest=speech_manifest,
+                noise_manifest=noise_manifest)
 
 
 def test_parser_extractor_rebuilder_match_oracle():
@@ -94,6 +108,20 @@ def test_tester_from_config_and_checkpoint(workdir, capsys):
         [n for i in range(3) for n in ("utt%d.wav" % i, "utt%d_mix.wav" % i, "utt%d_de.wav" % i)])
     de, _ = audio_io.load_wav(os.path.join(out_dir, "utt1_de.wav"), 8000)
     assert len(de) == 12345
+    # speech + noise manifests: item i is mixed with noise item i at snr dB, short items are dropped
+    np.random.seed(3)
+    ds = DataSet(workdir["speech_manifest"], workdir["noise_manifest"], sample_rate=8000, window_ms=32, stride_ms=16,
+                 snr=5.0, use_complex=True)
+    assert len(ds) == 3 and len(ds.noise_list) == 3
+    (mix, speech), (mix_spec, speech_spec) = ds[1]
+    assert len(mix) == len(speech) == 12345 and mix_spec.shape == speech_spec.shape == (129, 96)
+    snr = 10 * np.log10(np.sum(speech.astype(np.float64) ** 2) / np.sum((mix - speech).astype(np.float64) ** 2))
+    assert abs(snr - 5.0) < 1e-3
+    assert np.abs(mix_spec - stft.compute_spectrogram(mix.astype(np.float32), 8000, 0.032, 0.016, 256, True)).max() \
+        / np.abs(mix_spec).max() <= 1e-4
+    loader = DataLoader(ds, 2, sampler=None, num_works=4)
+    shapes = [(m.shape, len(ms)) for m, c, ms, cs in loader]
+    assert shapes == [((2, 124, 129, 1), 2), ((1, 62, 129, 1), 1)]
 
 
 def test_inference_engine_reshape_quirk_and_transpose(workdir):

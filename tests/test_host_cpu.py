@@ -226,3 +226,88 @@ def test_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _write_manifest(path, items):
+    import json
+    with open(path, "w") as f:
+        for it in items:
+            f.write(json.dumps(it) + "\n")
+
+
+def test_dataset_sampler_loader_follow_the_reference(tmp_path):
+    """Manifest filtering, clean/noise pairing, Sampler bins and SDR / AverageMeter arithmetic
+    (data_utils/data_loader.py:64-160, model_utils/utils.py:14-90 of the reference).  Where the
+    reference tree is present its own classes are run beside ours on the same seeded draws."""
+    from fullycnnspeechenhancement_b200.data_utils.data_loader import AudioParser, DataLoader, DataSet, Sampler
+    from fullycnnspeechenhancement_b200.model_utils.utils import SDR, AverageMeter
+    from oracle import ref_import
+    speech = str(tmp_path / "speech.manifest")
+    noise = str(tmp_path / "noise.manifest")
+    _write_manifest(speech, [{"audio_filepath": "s%d.wav" % i, "duration": d}
+                             for i, d in enumerate([0.3, 0.4, 1.0, 2.0, 5.0, 9.0, 0.39])])
+    _write_manifest(noise, [{"audio_filepath": "n%d.wav" % i, "duration": 1.0} for i in range(2)])
+    ds = DataSet(speech, noise, sample_rate=8000, min_duration=0.4, max_duration=5.0)
+    assert [it["audio_filepath"] for it in ds.item_list] == ["s1.wav", "s2.wav", "s3.wav", "s4.wav"]
+    assert [it["audio_filepath"] for it in ds.noise_list] == ["n0.wav", "n1.wav", "n0.wav", "n1.wav"]
+    assert ds() is ds and len(ds) == 4 and ds.item_name(2) == "s3.wav"
+    bad = str(tmp_path / "bad.manifest")
+    open(bad, "w").write("{not json}\n")
+    with pytest.raises(IOError):
+        DataSet(bad, None)
+    nodur = str(tmp_path / "nodur.manifest")
+    _write_manifest(nodur, [{"audio_filepath": "a.wav"}])
+    with pytest.raises(KeyError):
+        DataSet(nodur, None)
+    # waveform pairing without touching the STFT (no GPU here): patch the decoder
+    waves = {"s%d.wav" % i: np.random.default_rng(i).normal(size=900 + 100 * i).astype(np.float32) for i in range(7)}
+    waves.update({"n%d.wav" % i: np.random.default_rng(50 + i).normal(size=400 + 2000 * i).astype(np.float32) for i in range(2)})
+    ds.load_audio = lambda path: (waves[path], 8000)
+    ds.snr = 10.0
+    np.random.seed(7)
+    mix, clean = ds.load_pair(1)                       # s2 (1100 samples) + n1 (2400 samples: random crop)
+    assert clean is waves["s2.wav"] and len(mix) == 1100
+    got = 10 * np.log10(np.sum(clean.astype(np.float64) ** 2) / np.sum((mix - clean).astype(np.float64) ** 2))
+    assert abs(got - 10.0) < 1e-4
+    np.random.seed(7)
+    mix0, _ = ds.load_pair(0)                          # s1 (1000) + n0 (400: doubled twice, then cut)
+    assert len(mix0) == 1000
+    if ref_import.available():
+        RefParser = ref_import.load()[3]
+        rp = RefParser(sample_rate=8000, snr=10.0)
+        np.random.seed(7)
+        assert np.array_equal(rp.add_noise(waves["s2.wav"], waves["n1.wav"]), mix)
+        np.random.seed(7)
+        assert np.array_equal(rp.add_noise(waves["s1.wav"], waves["n0.wav"]), mix0)
+    # paired manifest
+    paired = str(tmp_path / "paired.manifest")
+    _write_manifest(paired, [{"clean_audio_filepath": "s0.wav", "mix_audio_filepath": "s1.wav", "duration": 1.0}])
+    dp = DataSet(paired, None, sample_rate=8000)
+    dp.load_audio = lambda path: (waves[path], 8000)
+    m, c = dp.load_pair(0)
+    assert m is waves["s1.wav"] and c is waves["s0.wav"] and dp.item_name(0) == "s0.wav"
+    # default loader bins and the Sampler's list surgery
+    ld = DataLoader(ds, 3)
+    assert ld.bins == [[0, 1, 2], [3]] and len(ld) == 2 and ld.num_works == 2
+    np.random.seed(0)
+    sm = Sampler(ds, 3)                                 # extends 4 items to 6 with the last two
+    assert len(ds) == 6 and [it["audio_filepath"] for it in ds.item_list[4:]] == ["s3.wav", "s4.wav"]
+    assert sorted(sorted(b) for b in sm) == [[0, 1, 2], [3, 4, 5]] and len(sm) == 2 and sm.iter_num() == 2
+    ds2 = DataSet(speech, None, sample_rate=8000, min_duration=0.0)
+    Sampler(ds2, 3, drop_last=True)
+    assert len(ds2) == 6
+    ds3 = DataSet(speech, None, sample_rate=8000, min_duration=0.0)
+    ds3.item_list = ds3.item_list[:6]
+    Sampler(ds3, 3)                                      # divides evenly: the reference still appends a whole batch
+    assert len(ds3) == 9
+    # scoring helpers
+    y = np.random.default_rng(1).normal(size=1000)
+    e = y + 0.01 * np.random.default_rng(2).normal(size=1000)
+    want = 10 * np.log10(np.power(y, 2).sum() / (np.power(e - y, 2).sum() + np.finfo(np.float32).eps))
+    assert SDR()(y, e) == want
+    assert np.isfinite(SDR()(y, y))                     # the epsilon keeps a perfect estimate finite
+    am = AverageMeter()
+    am.update(2.0)
+    am.update(4.0, n=3)
+    assert am.sum == 6.0 and am.count == 4 and am.avg == 1.5
+    assert AudioParser(8000, 32, 16).window_s == 0.032
