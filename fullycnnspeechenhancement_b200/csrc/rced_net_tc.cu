@@ -93,13 +93,42 @@ __device__ __forceinline__ uint32_t ld_acquire(uint32_t addr) {
 }
 // Both barriers complete: the two tests of a round are in flight together, so the wake-up costs one
 // test latency (~160 cycles) after the later arrival instead of two.
+#ifndef RCED_TC_EPIWAIT
+#define RCED_TC_EPIWAIT 1   // 1 (default) blocking try_wait after one test of both; experiment: 0 spin on test_wait, 2 test_wait + nanosleep
+#endif
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t bar_b, uint32_t parity, unsigned int* err, int code) {
+#if RCED_TC_EPIWAIT == 1
+    {
+        const bool a = mbar_test(bar_a, parity);
+        const bool b = mbar_test(bar_b, parity);
+        if (a && b) return;
+    }
+    for (int it = 0; it < (1 << 21); ++it) {
+        if (mbar_try(bar_a, parity) && mbar_try(bar_b, parity)) return;
+        if ((it & 63) == 63 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) return;
+    }
+#else
     for (int it = 0; it < (1 << 22); ++it) {
         const bool a = mbar_test(bar_a, parity);
         const bool b = mbar_test(bar_b, parity);
         if (a && b) return;
+#if RCED_TC_EPIWAIT == 2
+        __nanosleep(RCED_TC_EPISLEEP);
+#endif
         if ((it & 255) == 255 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) return;
     }
+#endif
     atomicMax(err, (unsigned int)code);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -135,6 +164,47 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // registers written by tcgen05.ld may only be read after tcgen05.wait::ld (see rced_net.cu)
 __device__ __forceinline__ void reg_fence8(float (&v)[8]) {
     asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
+}
+// skip scratch traffic with an L2 eviction-priority hint (RCED_TC_SKIPHINT: experiment switch)
+#ifndef RCED_TC_SKIPHINT
+#define RCED_TC_SKIPHINT 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld_hint4(const float4* p, uint64_t pol) {
+#if RCED_TC_SKIPHINT
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol)
+                 : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ void st_hint4(float4* p, const float4 v, uint64_t pol) {
+#if RCED_TC_SKIPHINT
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void st_hint1(float* p, const float v, uint64_t pol) {
+#if RCED_TC_SKIPHINT
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+    *p = v;
+#endif
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 
@@ -226,6 +296,7 @@ struct Ctx {
     float* skip;
     float* priv;        // this warp's row-space accumulator of the (1,129) layer [kRows]
     long long g0;
+    uint64_t pol_last, pol_first;   // L2 eviction-priority policies (skip scratch / streamed output)
 };
 
 __device__ __forceinline__ uint32_t bar_addr(const Ctx& c, int slot) { return c.bars + 8u * slot; }
@@ -257,8 +328,8 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
     // on the accumulator: the L2 latency of its first group hides behind the wait for the MMAs
     float4 sk0 = make_float4(0.f, 0.f, 0.f, 0.f), sk1 = sk0;
     if (e.add) {
-        sk0 = sp[0];
-        sk1 = sp[1];
+        sk0 = ld_hint4(sp, c.pol_last);
+        sk1 = ld_hint4(sp + 1, c.pol_last);
     }
     // Even and odd tiles are issued by two threads, each committing in its own order: this tile's
     // accumulator is complete with acc_full[t]; the neighbour tile's commit (other thread) also
@@ -297,13 +368,13 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
             tmem_ld8(ta + (g + 1) * 8, d1);
             tmem_ld8(ta + e.np + (g + 1) * 8, d2);
             if (e.add) {
-                sk0 = sp[(size_t)(g + 1) * kRows * 2];
-                sk1 = sp[(size_t)(g + 1) * kRows * 2 + 1];
+                sk0 = ld_hint4(sp + (size_t)(g + 1) * kRows * 2, c.pol_last);
+                sk1 = ld_hint4(sp + (size_t)(g + 1) * kRows * 2 + 1, c.pol_last);
             }
         }
         if (e.save_base >= 0) {
-            dp[(size_t)g * kRows * 2] = make_float4(v[0], v[1], v[2], v[3]);
-            dp[(size_t)g * kRows * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+            st_hint4(dp + (size_t)g * kRows * 2, make_float4(v[0], v[1], v[2], v[3]), c.pol_last);
+            st_hint4(dp + (size_t)g * kRows * 2 + 1, make_float4(v[4], v[5], v[6], v[7]), c.pol_last);
         }
         store_split8(c.act, g, kLead + r, v, valid);
     }
@@ -408,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char* act = smem;
-    int2* tab = reinterpret_cast<int2*>(smem + smem_tab_off(ARCH));
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + smem_tab_off(ARCH));
     int4* steps = reinterpret_cast<int4*>(smem + smem_step_off(ARCH));
     float* s_bias = reinterpret_cast<float*>(smem + smem_bias_off(ARCH));
     long long* bnd = reinterpret_cast<long long*>(smem + smem_bnd_off(ARCH));
@@ -437,19 +508,24 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kNextInSlot) = 0u;
     }
     for (int s = 0; s < NS; ++s) {
-        const int nu = step_units(ARCH, s), nc = step_chunks(ARCH, s), ub = unit_base(ARCH, s);
-        for (int u = threadIdx.x; u < nu; u += kThreads) {
-            const int o0 = chunk_off16(ARCH, s, 2 * u);
-            const int o1 = 2 * u + 1 < nc ? chunk_off16(ARCH, s, 2 * u + 1) : o0 + 1;   // dummy chunk: zero weights
-            // the finished low words of the unit's A (row tile 0, hi planes) and B descriptors: steps
-            // alternate between the two weight buffers and n_steps is even, so step s always uses buffer s & 1
+        const int nu = step_units(ARCH, s), nc = step_chunks(ARCH, s);
+        // Per step kTabStride words: the finished low words of the units' A descriptors (row tile 0,
+        // hi planes): start address and the distance to the unit's second K chunk.  Slots behind the
+        // last unit repeat unit 0 (they are loaded but never issued).
+        for (int u = threadIdx.x; u < kTabStride; u += kThreads) {
+            const int uu = u < nu ? u : 0;
+            const int o0 = chunk_off16(ARCH, s, 2 * uu);
+            const int o1 = 2 * uu + 1 < nc ? chunk_off16(ARCH, s, 2 * uu + 1) : o0 + 1;   // dummy chunk: zero weights
             const uint32_t a16 = (smem_u32(act) >> 4) + kLead + (uint32_t)o0;
-            const uint32_t w16 = (smem_u32(smem + smem_w_off(ARCH, s & 1)) >> 4) + (uint32_t)(u * (step_tile_bytes(ARCH, s) >> 4));
-            tab[ub + u] = make_int2((int)((a16 & 0x3FFFu) | ((uint32_t)(o1 - o0) << 16)),
-                                    (int)((w16 & 0x3FFFu) | ((uint32_t)step_tile_rows(ARCH, s) << 16)));
+            tab[s * kTabStride + u] = (a16 & 0x3FFFu) | ((uint32_t)(o1 - o0) << 16);
         }
-        if (threadIdx.x == 0)
-            steps[s] = make_int4(nu, ub, step_np(ARCH, s), (step_tile_bytes(ARCH, s) >> 4) | (is_final(ARCH, s) ? (1 << 16) : 0));
+        if (threadIdx.x == 0) {
+            // B descriptor of unit 0 (unit u is tile16 * u further): steps alternate between the two weight
+            // buffers and n_steps is even, so step s always uses buffer s & 1
+            const uint32_t w16 = smem_u32(smem + smem_w_off(ARCH, s & 1)) >> 4;
+            steps[s] = make_int4(nu, (int)((w16 & 0x3FFFu) | ((uint32_t)step_tile_rows(ARCH, s) << 16)), step_np(ARCH, s),
+                                 (step_tile_bytes(ARCH, s) >> 4) | (is_final(ARCH, s) ? (1 << 16) : 0));
+        }
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTiles; ++i) {
@@ -458,10 +534,10 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars + 8 * (kBarWFull + i), 1);
-            mbar_init(bars + 8 * (kBarWFree + i), 2);   // both issuing threads commit
+            mbar_init(bars + 8 * (kBarWFree + i), kIssuers);   // every issuing thread commits
         }
         mbar_init(bars + 8 * kBarInReady, kEpiWarps);
-        mbar_init(bars + 8 * kBarConvDone, 2);
+        mbar_init(bars + 8 * kBarConvDone, kIssuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -475,15 +551,17 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     const uint32_t tm = s_tmem;
     const long long NB = (p.total_rows + kFB - 1) / kFB;
 
-    if (warp == 0 || warp == 3) {
+    if (warp == 0 || warp == 3 || (kIssuers == 3 && warp == 5)) {
         // ================= MMA issue =================
-        // Two issuing threads (one elected lane of warp 0 and of warp 3) take the even and the odd row
-        // tiles: the tensor pipe accepts only a couple of instructions ahead of execution, so a
-        // single thread's work between two tiles (dependency check, descriptor set-up, commit) left
-        // the pipe idle; with two threads one prepares its tile while the other one issues.
+        // kIssuers issuing threads (one elected lane of warps 0, 3 and 5) take the row tiles of the
+        // global (step, tile) sequence round robin: the tensor pipe accepts only a couple of
+        // instructions ahead of execution, so the work of one thread between two tiles (dependency
+        // check, descriptor set-up, commit) or between two steps (the step prologue) would leave the
+        // pipe idle; with three threads and 8 tiles per step the step boundaries of the threads fall
+        // at different times, and one thread prepares while the others issue.
         // Per step the start-address words of every unit's A and B descriptors are built once into
         // registers (fully unrolled, kMaxUnits slots): issuing a unit is an add and the MMA pair.
-        const int t_first = warp == 0 ? 0 : 1;
+        const int iss = warp == 0 ? 0 : (warp == 3 ? 1 : 2);
         if (elect_one()) {
             const uint32_t flag = bars + 8 * kFlagSlot;
             uint32_t seen = 0;   // last value read from the scout's counter
@@ -497,15 +575,24 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                     const int4 st = steps[s];
                     const int nu = st.x, np = st.z;
                     const bool fin = (st.w >> 16) != 0;
-                    const int2* ut = tab + st.y;
                     const uint32_t id_a = idesc_f16(fin ? np : 2 * np), id_b = idesc_f16(np);
-                    uint32_t ua[kMaxUnits];   // A descriptor low words, built at kernel start
+                    uint32_t ua[kMaxUnits];   // A descriptor low words, built at kernel start: five 16-byte loads
+                    {
+                        const uint4* ut = reinterpret_cast<const uint4*>(tab + s * kTabStride);
 #pragma unroll
-                    for (int u = 0; u < kMaxUnits; ++u) ua[u] = (uint32_t)ut[u < nu ? u : 0].x;
-                    const uint32_t ub0 = (uint32_t)ut[0].y;             // B descriptor of unit 0; unit u is tile16 * u further
+                        for (int q = 0; q < kTabStride / 4; ++q) {
+                            const uint4 w = ut[q];
+                            if (4 * q + 0 < kMaxUnits) ua[4 * q + 0] = w.x;
+                            if (4 * q + 1 < kMaxUnits) ua[4 * q + 1] = w.y;
+                            if (4 * q + 2 < kMaxUnits) ua[4 * q + 2] = w.z;
+                            if (4 * q + 3 < kMaxUnits) ua[4 * q + 3] = w.w;
+                        }
+                    }
+                    const uint32_t ub0 = (uint32_t)st.y;             // B descriptor of unit 0; unit u is tile16 * u further
                     const uint32_t tile16 = (uint32_t)(st.w & 0xFFFF);
+                    const int t_first = (iss + kIssuers - (int)((k * kTiles) % kIssuers)) % kIssuers;
 #pragma unroll 1
-                    for (int t = t_first; t < kTiles; t += 2) {
+                    for (int t = t_first; t < kTiles; t += kIssuers) {
                         // the scout (warp 2) has waited on this tile's mbarriers and published its index: a
                         // shared-memory load costs ~30 cycles where an mbarrier test costs ~160 (umma_probe
                         // lat), and it is only needed when the last value seen does not cover this tile
@@ -650,6 +737,8 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         c.et = (warp - kCtrlWarps) * 32 + lane;
         c.skip = p.skip + (size_t)blockIdx.x * skip_floats_per_cta(ARCH);
         c.priv = priv_base(act, warp - kCtrlWarps);
+        c.pol_last = l2_policy_evict_last();
+        c.pol_first = l2_policy_evict_first();
         float amax = 0.f;
         const float bias_f = s_bias[(NL - 1) * 32];
         uint32_t it = 0;
@@ -705,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                     float acc = 0.f;
 #pragma unroll
                     for (int w = 0; w < kEpiWarps; ++w) acc += priv_base(act, w)[fi * kFS + b];
-                    p.out[(g0 + fi) * kBins + b] = acc + bias_f;
+                    st_hint1(p.out + (g0 + fi) * kBins + b, acc + bias_f, c.pol_first);
                 }
             }
         }

@@ -29,7 +29,11 @@ constexpr int kActBytes = 2 * kPlanes * kPlane16 * 16;
 constexpr int kAccCols = 64;                  // tensor-memory columns per tile
 constexpr int kFinalTaps = 48;                // taps of the (1,129) layer per pass (N of the pass)
 constexpr int kFinalPasses = 3;
-constexpr int kCtrlWarps = 5;                 // warps 0 / 3: MMA issue of the even / odd row tiles, 1: weight producer, 2: dependency scout,
+#ifndef RCED_TC_ISSUERS
+#define RCED_TC_ISSUERS 3
+#endif
+constexpr int kIssuers = RCED_TC_ISSUERS;     // MMA-issuing threads (2 or 3)
+constexpr int kCtrlWarps = kIssuers == 3 ? 6 : 5;   // warps 0 / 3 / 5: MMA issue (row tiles round robin), 1: weight producer, 2: dependency scout,
                                               // 4: prefetch of the next batch's utterance bounds and input rows
 constexpr int kEpiWarps = 16;                 // groups of four warps (one per tensor-memory lane quadrant)
 constexpr int kGroups = kEpiWarps / 4;        // group g takes the row tiles t = g, g + kGroups, ...
@@ -85,6 +89,7 @@ RCED_HD constexpr int max_units(int arch) {
     return m;
 }
 constexpr int kMaxUnits = 18;   // register slots of the MMA issue loop
+constexpr int kTabStride = 20;  // words per step in the A-descriptor table (kMaxUnits rounded up to 16 bytes)
 static_assert(n_steps(1) % 2 == 0 && n_steps(2) % 2 == 0 && n_steps(3) % 2 == 0, "step s must always use weight buffer s & 1");
 static_assert(max_units(1) <= kMaxUnits && max_units(2) <= kMaxUnits && max_units(3) <= kMaxUnits, "raise kMaxUnits");
 
@@ -113,8 +118,8 @@ RCED_HD constexpr size_t skip_floats_per_cta(int arch) { return (size_t)skip_c8_
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------
 RCED_HD constexpr int pad128(int x) { return (x + 127) & ~127; }
 RCED_HD constexpr int smem_w_off(int arch, int buf) { return kActBytes + buf * pad128(max_step_w_bytes(arch)); }
-RCED_HD constexpr int smem_tab_off(int arch) { return smem_w_off(arch, 2); }                        // int2[total_units]
-RCED_HD constexpr int smem_step_off(int arch) { return smem_tab_off(arch) + pad128(8 * total_units(arch)); }   // int4[n_steps]
+RCED_HD constexpr int smem_tab_off(int arch) { return smem_w_off(arch, 2); }                        // uint32[n_steps][kTabStride]
+RCED_HD constexpr int smem_step_off(int arch) { return smem_tab_off(arch) + pad128(4 * kTabStride * n_steps(arch)); }   // int4[n_steps]
 RCED_HD constexpr int smem_bias_off(int arch) { return smem_step_off(arch) + pad128(16 * n_steps(arch)); }     // float[n_steps][32]
 RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 128 * n_steps(arch); }             // float[kFB][kOutStride]
 RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + pad128(4 * kFB * kOutStride); }     // long long[2][kFB][2]

@@ -1,0 +1,103 @@
+// Timing harness for the tensor-core network kernel (K2-TC) alone: compiles csrc/rced_net_tc.cu
+// into this translation unit (so that -D experiment switches apply), packs seeded random weights
+// and times the BASELINE configs[1] launch (1024 x 249 frames).  Prints a checksum of the output
+// so that experiment variants can be compared with each other (parity itself is tests/).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr \
+//        -I../fullycnnspeechenhancement_b200/csrc -o k2tc_bench k2tc_bench.cu && ./k2tc_bench [arch] [label] [trace file]
+#include "../fullycnnspeechenhancement_b200/csrc/rced_net_tc.cu"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+namespace rced {
+void count_launch(int) {}
+}  // namespace rced
+
+int main(int argc, char** argv) {
+    using namespace rced;
+    const int arch = argc > 1 ? atoi(argv[1]) : 2;
+    const char* label = argc > 2 ? argv[2] : "";
+    const char* trace_path = argc > 3 ? argv[3] : nullptr;
+    const int n_utt = 1024, T = 249;
+    const long long rows = (long long)n_utt * T;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, 0);
+    const int nsm = prop.multiProcessorCount;
+    const long long nf = arch == 1 ? folded_count(1) : arch == 2 ? folded_count(2) : folded_count(3);
+    std::vector<float> w((size_t)nf);
+    srand(1);
+    // Glorot-like scale per layer keeps the activations of 16 layers in range
+    for (int li = 0; li < num_layers(arch); ++li) {
+        const LSpec sp = spec(arch, li);
+        const long long o = folded_off(arch, li), n = (long long)sp.kh * sp.kw * sp.cin * sp.cout;
+        const float lim = sqrtf(6.f / (float)(sp.kh * sp.kw * (sp.cin + sp.cout)));
+        for (long long i = 0; i < n; ++i) w[o + i] = lim * (2.f * (float)rand() / RAND_MAX - 1.f);
+        for (int i = 0; i < sp.cout; ++i) w[o + n + i] = 0.01f * ((float)rand() / RAND_MAX - 0.5f);
+    }
+    std::vector<unsigned char> img((size_t)tc_image_bytes(arch));
+    std::vector<float> bias((size_t)tc_bias_floats(arch));
+    tc_pack_weights(arch, w.data(), img.data(), bias.data());
+    std::vector<float> x((size_t)rows * kBins);
+    for (auto& v : x) v = (float)rand() / RAND_MAX;
+    std::vector<long long> ro(n_utt + 1);
+    for (int i = 0; i <= n_utt; ++i) ro[i] = (long long)i * T;
+    unsigned char* dimg;
+    float *dbias, *dx, *dy, *dskip;
+    long long *dro, *dtrace = nullptr;
+    unsigned int* dflags;
+    cudaMalloc(&dimg, img.size());
+    cudaMalloc(&dbias, bias.size() * 4);
+    cudaMalloc(&dx, x.size() * 4);
+    cudaMalloc(&dy, x.size() * 4);
+    cudaMalloc(&dro, ro.size() * 8);
+    cudaMalloc(&dskip, (size_t)nsm * tc_skip_floats_per_cta(arch) * 4);
+    cudaMalloc(&dflags, 8);
+    cudaMemset(dflags, 0, 8);
+    cudaMemcpy(dimg, img.data(), img.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(dbias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dro, ro.data(), ro.size() * 8, cudaMemcpyHostToDevice);
+    const int slots = tc_trace_slots(arch);
+    if (trace_path) {
+        cudaMalloc(&dtrace, slots * 8);
+        cudaMemset(dtrace, 0, slots * 8);
+    }
+    NetParams p;
+    p.packed = nullptr; p.in = dx; p.out = dy; p.row_off = dro; p.n_utt = n_utt; p.total_rows = rows; p.skip_scratch = nullptr; p.guard = nullptr;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(a);
+        cudaError_t e = launch_net_tc(arch, p, dimg, dbias, dskip, dflags, r == 4 ? dtrace : nullptr, nsm, 0);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 1; }
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        if (r > 0 && r < 4 && ms < best) best = ms;
+    }
+    std::vector<float> y(x.size());
+    cudaMemcpy(y.data(), dy, y.size() * 4, cudaMemcpyDeviceToHost);
+    unsigned int fl[2];
+    cudaMemcpy(fl, dflags, 8, cudaMemcpyDeviceToHost);
+    double s = 0, sa = 0;
+    for (size_t i = 0; i < y.size(); ++i) { s += y[i]; sa += fabs((double)y[i]); }
+    float amax;
+    memcpy(&amax, &fl[0], 4);
+    const double mac = arch == 1 ? (double)mac_per_frame(1, true) : arch == 2 ? (double)mac_per_frame(2, true) : (double)mac_per_frame(3, true);
+    printf("%-14s arch %d: %.3f ms, %.1f TFLOP/s valid-tap, %.1f k audio-s/s | sum %.9e abs %.9e amax %.4f err %u\n", label, arch, best,
+           2.0 * mac * rows / (best * 1e-3) / 1e12, n_utt * 4.0 / best, s, sa, amax, fl[1]);
+    if (dtrace) {
+        std::vector<long long> t(slots);
+        cudaMemcpy(t.data(), dtrace, slots * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(trace_path, "w")) {
+            for (int i = 0; i < slots; ++i) fprintf(f, "%lld%c", t[i], (i + 1) % tc::kTraceEvents == 0 ? '\n' : ' ');
+            fclose(f);
+        }
+    }
+    return 0;
+}
