@@ -196,7 +196,7 @@ def roofline(variant, achieved, ffma_peak, flops_valid, k2_ms, share, traffic, r
         return common
     pk = measured_peaks()
     # tensor-core work actually issued: per 128-row tile and unit (two (tap, 8-channel) chunks,
-    # K = 16) A_hi x [Whi|Wlo] (N = 2 NP) and A_lo x Whi (N = NP); 8 tiles per 7-frame batch; output layer 3 passes
+    # K = 16) A_hi x [Whi|Wlo] (N = 2 NP) and A_lo x Whi (N = NP); 8 tiles per 7-frame batch; output layer 5 row-shifted blocks
     import ctypes as ct
     from fullycnnspeechenhancement_b200 import _lib
     out = (ct.c_int64 * 4096)()
@@ -204,10 +204,10 @@ def roofline(variant, achieved, ffma_peak, flops_valid, k2_ms, share, traffic, r
     ns = out[0]
     mac_tile, cyc_tile = 0, 0.0
     for st in range(ns):
-        units, npad, final = out[12 + 6 * st], out[14 + 6 * st], out[17 + 6 * st]
-        if final:
-            mac_tile += units * 3 * 128 * npad * 16
-            cyc_tile += units * 3 * (32 + npad / 4.0)
+        units, npad, final = out[16 + 6 * st], out[18 + 6 * st], out[21 + 6 * st]
+        if final:   # row-shifted blocks x 3 products, for the even- and the odd-frame copy (14 of 16 tile-parity pairs)
+            mac_tile += 1.75 * units * 3 * 128 * npad * 16
+            cyc_tile += 1.75 * units * 3 * (32 + npad / 4.0)
         else:
             mac_tile += units * 128 * 16 * 3 * npad
             cyc_tile += units * ((32 + 2 * npad / 4.0) + (32 + npad / 4.0))

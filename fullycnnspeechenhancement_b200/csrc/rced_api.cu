@@ -378,7 +378,7 @@ int rced_tc_pack_weights(int arch, const float* folded, size_t n_folded, void* i
 int rced_tc_layout(int arch, int64_t* out, int n) {
     if (!arch_ok(arch) || !out) return fail(RCED_ERR_ARG, "bad argument");
     const int ns = tc::n_steps(arch), nu = tc::total_units(arch);
-    if (n < 12 + 6 * ns + 2 * nu) return fail(RCED_ERR_ARG, "output too small");
+    if (n < 16 + 6 * ns + 2 * nu) return fail(RCED_ERR_ARG, "output too small");
     out[0] = ns;
     out[1] = nu;
     out[2] = tc::w_image_bytes(arch);
@@ -389,10 +389,13 @@ int rced_tc_layout(int arch, int64_t* out, int n) {
     out[7] = tc::kFB;
     out[8] = tc::kTiles;
     out[9] = tc::kLo16;
-    out[10] = tc::kFinalTaps;
+    out[10] = tc::kFinalN;
     out[11] = (int64_t)tc::skip_floats_per_cta(arch);
+    out[12] = tc::kFinalShifts;
+    out[13] = tc::kFrontRows;
+    out[14] = out[15] = 0;
     for (int s = 0; s < ns; ++s) {
-        int64_t* o = out + 12 + 6 * s;
+        int64_t* o = out + 16 + 6 * s;
         o[0] = tc::step_units(arch, s);
         o[1] = tc::unit_base(arch, s);
         o[2] = tc::step_np(arch, s);
@@ -400,13 +403,11 @@ int rced_tc_layout(int arch, int64_t* out, int n) {
         o[4] = tc::step_w_off(arch, s);
         o[5] = tc::is_final(arch, s) ? 1 : 0;
     }
-    int64_t* u = out + 12 + 6 * ns;
+    int64_t* u = out + 16 + 6 * ns;
     for (int s = 0; s < ns; ++s)
         for (int i = 0; i < tc::step_units(arch, s); ++i) {
-            const int o0 = tc::chunk_off16(arch, s, 2 * i);
-            const int o1 = 2 * i + 1 < tc::step_chunks(arch, s) ? tc::chunk_off16(arch, s, 2 * i + 1) : o0 + 1;
-            u[2 * (tc::unit_base(arch, s) + i)] = o0;
-            u[2 * (tc::unit_base(arch, s) + i) + 1] = o1 - o0;
+            u[2 * (tc::unit_base(arch, s) + i)] = tc::unit_off16(arch, s, i);
+            u[2 * (tc::unit_base(arch, s) + i) + 1] = tc::unit_lbo16(arch, s, i);
         }
     return RCED_OK;
 }

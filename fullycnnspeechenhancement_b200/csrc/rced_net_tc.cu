@@ -20,9 +20,12 @@
 //    layer's planes).  Layers overlap tile by tile: the epilogue of (layer, tile t) starts when
 //    the MMAs of tile t+1 have completed (they read tile t's halo rows, planes are updated in
 //    place) and the MMAs of (layer+1, t) start when the epilogues of tiles t-1..t+1 are done;
-//  * the (1,129) output layer runs "taps in N": D[row][tap] = A[row][cin] * Wf[tap][cin] in three
-//    passes of 48 taps; the epilogue adds D[row b][tap j] into out[b - j + 64] of the row's frame
-//    (a shuffle-skewed diagonal sum per warp, fixed order) -- no 64-row halo is ever materialised;
+//  * the (1,129) output layer runs "taps in N with row-shifted accumulation" (rced_tc.cuh): five MMAs
+//    per row tile whose A descriptors are shifted by -64 .. +64 rows accumulate E[r][n] =
+//    sum_i X[r + 32 (i - 2)] . W[32 i + n] into 32 columns, and the epilogue forms out[b] =
+//    sum_n E[b + n][n] with one shuffle per column (fixed order).  The shifts would reach the
+//    neighbouring frames, so the last conv layer writes an even-frames-only and an odd-frames-only
+//    copy of its output and each parity has its own accumulator columns;
 //  * skip tensors go to a per-CTA FP32 scratch in global memory (L2 resident);
 //  * range guard: FP16 overflows beyond 65504.  The kernel records the largest |activation| it
 //    stored; rced_forward re-runs the batch with the FP32 FFMA kernel when the guard tripped.
@@ -50,7 +53,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+#ifdef RCED_TC_DIAG_RELAXED
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+#else
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+#endif
 }
 // Bounded wait: a protocol error must end the kernel with an error flag, not hang the GPU.  Once
 // any wait has timed out every other wait of the grid gives up at its next check of the flag.
@@ -107,22 +114,28 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t bar_b, uint32_t parity, unsigned int* err, int code) {
+// Three barriers complete (two of them may be the same): the tests of a round are in flight together,
+// so the common case costs one test latency (~160 cycles); what is not complete yet is waited for
+// with the blocking try_wait, which does not take issue slots from the MMA-issuing warps.
+__device__ __forceinline__ void mbar_wait3(uint32_t bar_a, uint32_t bar_b, uint32_t bar_c, uint32_t parity, unsigned int* err, int code) {
 #if RCED_TC_EPIWAIT == 1
-    {
-        const bool a = mbar_test(bar_a, parity);
-        const bool b = mbar_test(bar_b, parity);
-        if (a && b) return;
-    }
+    bool a = mbar_test(bar_a, parity);
+    bool b = mbar_test(bar_b, parity);
+    bool c = mbar_test(bar_c, parity);
+    if (a && b && c) return;
     for (int it = 0; it < (1 << 21); ++it) {
-        if (mbar_try(bar_a, parity) && mbar_try(bar_b, parity)) return;
+        if (!a) a = mbar_try(bar_a, parity);
+        if (!b) b = mbar_try(bar_b, parity);
+        if (!c) c = mbar_try(bar_c, parity);
+        if (a && b && c) return;
         if ((it & 63) == 63 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) return;
     }
 #else
     for (int it = 0; it < (1 << 22); ++it) {
         const bool a = mbar_test(bar_a, parity);
         const bool b = mbar_test(bar_b, parity);
-        if (a && b) return;
+        const bool c = mbar_test(bar_c, parity);
+        if (a && b && c) return;
 #if RCED_TC_EPIWAIT == 2
         __nanosleep(RCED_TC_EPISLEEP);
 #endif
@@ -166,12 +179,19 @@ __device__ __forceinline__ void reg_fence8(float (&v)[8]) {
     asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
 }
 // skip scratch traffic with an L2 eviction-priority hint (RCED_TC_SKIPHINT: experiment switch)
+#ifndef RCED_TC_MAXINFLIGHT
+#define RCED_TC_MAXINFLIGHT 0   // experiment switch: row tiles being issued concurrently (0: no limit; a limit of 1 / 2 costs 2x / 25 %)
+#endif
 #ifndef RCED_TC_SKIPHINT
 #define RCED_TC_SKIPHINT 0
 #endif
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t pol;
+#if RCED_TC_SKIPHINT == 2   // the hinted instruction forms with the default priority (experiment)
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+#else
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
     return pol;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -241,12 +261,23 @@ __device__ __forceinline__ void store_split8(unsigned char* act, int cg, int q, 
     }
 }
 
-// Row-space accumulators of the output layer, one per epilogue warp (kRows floats): they overlay
-// planes 2 and 3, which are dead by then -- warps 0..7 in the hi planes, 8..15 in the lo planes.
-__device__ __forceinline__ float* priv_base(unsigned char* act, int ew) {
-    return reinterpret_cast<float*>(act + ((ew >> 3) * kLo16 + 2 * kPlane16) * 16) + (ew & 7) * kRows;
+// The last conv layer feeds the row-shifted output layer: its rows are stored twice, in planes
+// (0, 1) if the row's frame index is even and in planes (2, 3) if it is odd, zeros in the other pair
+__device__ __forceinline__ void store_split8_parity(unsigned char* act, int cg, int q, const float (&v)[8], bool valid, int odd) {
+    uint4 h, l;
+    split2(v[0], v[1], h.x, l.x);
+    split2(v[2], v[3], h.y, l.y);
+    split2(v[4], v[5], h.z, l.z);
+    split2(v[6], v[7], h.w, l.w);
+    if (!valid) h = l = make_uint4(0, 0, 0, 0);
+    uint4* pe = reinterpret_cast<uint4*>(act) + cg * kPlane16 + q;   // even-frame copy
+    uint4* po = pe + 2 * kPlane16;                                   // odd-frame copy
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    pe[0] = odd ? z : h;
+    pe[kLo16] = odd ? z : l;
+    po[0] = odd ? h : z;
+    po[kLo16] = odd ? l : z;
 }
-static_assert(8 * kRows * 4 <= 2 * kPlane16 * 16 && kEpiWarps <= 16, "per-warp accumulators must fit planes 2 and 3");
 
 struct TcParams {
     const unsigned char* wimg;   // weight image (global): per step, per unit, [2][rows][8] halfs
@@ -277,7 +308,8 @@ struct EpiStep {
     int add;       // 0 none, 1 before the ReLU, 2 after it (V3)
     int add_base;  // first 8-channel group of the skip slot added
     int save_base; // first 8-channel group of the skip slot saved (-1: none)
-    int pad0, pad1;
+    int last;      // the last conv layer: even / odd frame copies for the output layer
+    int pad1;
 };
 static_assert(sizeof(EpiStep) == 32, "EpiStep layout");
 
@@ -294,7 +326,7 @@ struct Ctx {
     bool tracing;
     int lane, quad, grp, et, nf;
     float* skip;
-    float* priv;        // this warp's row-space accumulator of the (1,129) layer [kRows]
+    float* outp;        // [2][kRows]: the two partial sums of every output row of the (1,129) layer
     long long g0;
     uint64_t pol_last, pol_first;   // L2 eviction-priority policies (skip scratch / streamed output)
 };
@@ -316,26 +348,47 @@ __device__ __forceinline__ void locate(const long long* __restrict__ row_off, in
 // epilogue of one conv layer for one row tile (runtime-parameterised, see EpiStep)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const int t, const uint32_t par, float& amax) {
-    const EpiStep e = c.epi[s];
+    EpiStep e = c.epi[s];
+#ifdef RCED_TC_DIAG_NOSKIP   // diagnosis only (wrong results): no skip traffic
+    e.add = 0;
+    e.save_base = -1;
+#endif
+#ifdef RCED_TC_DIAG_NOSAVE
+    e.save_base = -1;
+#endif
+#ifdef RCED_TC_DIAG_NOADD
+    e.add = 0;
+#endif
     const int r = t * 128 + c.quad * 32 + c.lane;   // row in tile space
     const int fi = r / kFS, b = r - fi * kFS;
     const bool valid = fi < c.nf && b < kBins;
     const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
-    const float4* sp = reinterpret_cast<const float4*>(c.skip) + ((size_t)e.add_base * kRows + r) * 2;
-    float4* dp = reinterpret_cast<float4*>(c.skip) + ((size_t)(e.save_base < 0 ? 0 : e.save_base) * kRows + r) * 2;
-
-    // the skip tensor (this thread's own row, written by this thread layers ago) does not depend
-    // on the accumulator: the L2 latency of its first group hides behind the wait for the MMAs
+    // Skip tensors: FP32 in a per-CTA global scratch (L2), [group of 8 channels][half][row][4 floats], so
+    // that a warp's 16-byte accesses cover whole sectors.  The row is saved and added by the same thread.
+    const float4* sp = reinterpret_cast<const float4*>(c.skip) + ((size_t)e.add_base * 2 * kRows + r);
+    float4* dp = reinterpret_cast<float4*>(c.skip) + ((size_t)(e.save_base < 0 ? 0 : e.save_base) * 2 * kRows + r);
+    // the skip row does not depend on the accumulator: the L2 latency of its first group hides behind
+    // the wait for the MMAs
+#ifdef RCED_TC_DIAG_VALIDROWS   // measured: predicating the skip traffic on valid rows costs more than the 12 % of bytes it saves
+    const bool do_add = e.add != 0 && valid, do_save = e.save_base >= 0 && valid;
+#else
+    const bool do_add = e.add != 0, do_save = e.save_base >= 0;
+#endif
     float4 sk0 = make_float4(0.f, 0.f, 0.f, 0.f), sk1 = sk0;
-    if (e.add) {
+    if (do_add) {
         sk0 = ld_hint4(sp, c.pol_last);
-        sk1 = ld_hint4(sp + 1, c.pol_last);
+        sk1 = ld_hint4(sp + kRows, c.pol_last);
     }
-    // Even and odd tiles are issued by two threads, each committing in its own order: this tile's
-    // accumulator is complete with acc_full[t]; the neighbour tile's commit (other thread) also
-    // covers that thread's earlier tile on the other side -- so nobody reads this tile's rows as
-    // a halo any more and the planes can be updated in place
-    mbar_wait2(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t - 1)), par, c.err, 100 + s);
+    // The planes are updated in place: this tile's rows are read by its own MMAs and, as halo, by the
+    // MMAs of both neighbour tiles.  The tiles are issued by different threads, each committing in its
+    // own order, so all three commits are waited for.
+#ifdef RCED_TC_DIAG_WAIT2   // diagnosis only (unsafe): without the commit of the tile before
+    mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t - 1)),
+               bar_addr(c, kBarAccFull + t), par, c.err, 100 + s);
+#else
+    mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t)),
+               bar_addr(c, kBarAccFull + (t > 0 ? t - 1 : t)), par, c.err, 100 + s);
+#endif
     fence_after();
     stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 2);
 
@@ -367,16 +420,17 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
         if (g + 1 < e.cg) {
             tmem_ld8(ta + (g + 1) * 8, d1);
             tmem_ld8(ta + e.np + (g + 1) * 8, d2);
-            if (e.add) {
-                sk0 = ld_hint4(sp + (size_t)(g + 1) * kRows * 2, c.pol_last);
-                sk1 = ld_hint4(sp + (size_t)(g + 1) * kRows * 2 + 1, c.pol_last);
+            if (do_add) {
+                sk0 = ld_hint4(sp + (size_t)(g + 1) * 2 * kRows, c.pol_last);
+                sk1 = ld_hint4(sp + (size_t)(g + 1) * 2 * kRows + kRows, c.pol_last);
             }
         }
-        if (e.save_base >= 0) {
-            st_hint4(dp + (size_t)g * kRows * 2, make_float4(v[0], v[1], v[2], v[3]), c.pol_last);
-            st_hint4(dp + (size_t)g * kRows * 2 + 1, make_float4(v[4], v[5], v[6], v[7]), c.pol_last);
+        if (do_save) {
+            st_hint4(dp + (size_t)g * 2 * kRows, make_float4(v[0], v[1], v[2], v[3]), c.pol_last);
+            st_hint4(dp + (size_t)g * 2 * kRows + kRows, make_float4(v[4], v[5], v[6], v[7]), c.pol_last);
         }
-        store_split8(c.act, g, kLead + r, v, valid);
+        if (e.last) store_split8_parity(c.act, g, kLead + r, v, valid, fi & 1);
+        else store_split8(c.act, g, kLead + r, v, valid);
     }
     fence_before();       // tcgen05.ld of this accumulator ordered before the barrier
     fence_async_smem();   // plane writes visible to the tensor core (async proxy)
@@ -385,62 +439,55 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
     stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 4);
 }
 
-// Epilogue of one pass of the (1,129) layer for one row tile.  D[row r][tap] belongs to output
-// row r - tap + 64 (same frame only): the warp sums its 32 x 48 block along the diagonals with one
-// shuffle per tap -- lane m collects the diagonals d = tap - lane in {m - 32, m, m + 32} -- and adds
-// the three sums to its private row-space accumulator (no atomics, fixed summation order).
+// Epilogue of the (1,129) layer for one row tile.  E[row r][n] (32 columns per frame parity) belongs
+// to output row r - n: the warp sums its 32 x 32 block along the diagonals with one shuffle per
+// column -- lane m collects the diagonals r - n = r0 + m (columns n < 32 - m, from lanes m + n) and
+// r0 + m - 32 (the other columns) -- and stores the two sums: every output row receives exactly one
+// sum from the warp that owns its 32-row block (outp[0]) and one from the next block (outp[1]).
+// E rows that belong to no frame of the parity, and diagonals that leave the frame, only ever
+// reach rows of the other parity or halo rows, which are not stored.
 template <int ARCH>
-__device__ __forceinline__ void epi_final_tile(const Ctx& c, const int pass, const int t, const uint32_t par) {
-    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 300 + pass);
+__device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const uint32_t par) {
+    constexpr int s = num_layers(ARCH) - 1;
+    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 300);
     fence_after();
-    stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, num_layers(ARCH) - 1 + pass, t, 2);
+    stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 2);
     const int r0 = t * 128 + c.quad * 32;
-    const int r = r0 + c.lane;
-    const int fi = r / kFS, b = r - fi * kFS;
-    const bool valid = fi < c.nf && b < kBins;
     const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
-    // tap = 48 pass + i stays inside the frame iff 0 <= b - tap + 64 <= 128: a contiguous range of
-    // i, kept as a bit mask so that the per-value test is one bit test
-    unsigned long long vmask = 0ull;
-    if (valid) {
-        const int ilo = b - 64 - pass * kFinalTaps, ihi = ilo + 128;
-        const int lo = ilo < 0 ? 0 : ilo, hi = ihi > kFinalTaps - 1 ? kFinalTaps - 1 : ihi;
-        if (lo <= hi) vmask = (~0ull >> (63 - hi)) & (~0ull << lo);
-    }
-    // running sums over the taps: s0 takes the values of diagonal m - 32 (i < lane), s1 those of
-    // m - 32 and m (i < lane + 32), tot everything; the three diagonals are differences of them
-    float s0 = 0.f, s1 = 0.f, tot = 0.f;
-    float d[8];
-    tmem_ld8(ta, d);
+    // rows this lane stores to: own block / previous block
+    const int ra = r0 + c.lane, rb = ra - 32;
+    const int fa = ra / kFS, fb = rb >= 0 ? rb / kFS : 0;
+    const bool va = fa < c.nf && ra - fa * kFS < kBins;
+    const bool vb = rb >= 0 && fb < c.nf && rb - fb * kFS < kBins;
 #pragma unroll 1
-    for (int g = 0; g < kFinalTaps / 8; ++g) {
-        tmem_wait_ld();
-        reg_fence8(d);
-        const uint32_t mb = (uint32_t)(vmask >> (8 * g));
-        float v[8];
+    for (int odd = 0; odd < 2; ++odd) {
+        if (odd && (t == 0 || t == kTiles - 1)) break;   // no odd frame reaches the first or the last row tile
+        float v[kFinalN];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (mb & (1u << e)) ? d[e] : 0.f;
-        if (g + 1 < kFinalTaps / 8) tmem_ld8(ta + (g + 1) * 8, d);
-        const int base = g * 8 - c.lane;   // i - lane of e = 0; shfl takes the source lane modulo 32
+        for (int g = 0; g < kFinalN / 8; ++g) {
+            float d[8];
+            tmem_ld8(ta + odd * kFinalN + g * 8, d);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float x = __shfl_sync(0xffffffffu, v[e], base + e);   // value of lane (i - m) mod 32
-            tot += x;
-            if (base + e < 32) s1 += x;
-            if (base + e < 0) s0 += x;
+            for (int e = 0; e < 8; ++e) v[g * 8 + e] = d[e];
         }
+        tmem_wait_ld();
+#pragma unroll
+        for (int n = 0; n < kFinalN; ++n) asm volatile("" : "+f"(v[n])::"memory");
+        float tot = 0.f, own = 0.f;
+#pragma unroll
+        for (int n = 0; n < kFinalN; ++n) {
+            const float x = __shfl_sync(0xffffffffu, v[n], c.lane + n);   // source lane (m + n) mod 32
+            tot += x;
+            if (c.lane + n < 32) own += x;
+        }
+        if (va && (fa & 1) == odd) c.outp[ra] = own;
+        if (vb && (fb & 1) == odd) c.outp[kRows + rb] = tot - own;
     }
-    const float am = s0, a0 = s1 - s0, ap = tot - s1;
-    // output row of diagonal d: r0 + 64 - 48 pass - d
-    float* pw = c.priv;
-    const int ro = r0 + 64 - pass * kFinalTaps - c.lane;
-    if (ro + 32 >= 0 && ro + 32 < kRows) pw[ro + 32] += am;
-    if (ro >= 0 && ro < kRows) pw[ro] += a0;
-    if (ro - 32 >= 0 && ro - 32 < kRows) pw[ro - 32] += ap;
+    if (c.tracing && c.quad == 0 && c.lane == 0) stamp(c.trace, true, s, t, 3);
     fence_before();
     __syncwarp();
     if (c.lane == 0) mbar_arrive(bar_addr(c, kBarActReady + t));
-    stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, num_layers(ARCH) - 1 + pass, t, 4);
+    stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 4);
 }
 
 // all steps of one batch for this epilogue warp
@@ -453,17 +500,9 @@ __device__ __forceinline__ void epi_steps(const Ctx& c, const uint32_t k0, float
 #pragma unroll 1
         for (int t = c.grp; t < kTiles; t += kGroups) epi_conv_tile(c, s, t, par, amax);
     }
-    // planes 2 and 3 are dead once the MMAs of the last conv layer have completed: they now hold
-    // the per-warp accumulators of the output layer
-    mbar_wait(bar_addr(c, kBarConvDone), (uint32_t)(k0 / n_steps(ARCH)) & 1, c.err, 400);
-    for (int i = c.lane; i < kRows / 4; i += 32) reinterpret_cast<float4*>(c.priv)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
+    const uint32_t par = (k0 + NL - 1) & 1;
 #pragma unroll 1
-    for (int pass = 0; pass < kFinalPasses; ++pass) {
-        const uint32_t par = (k0 + NL - 1 + pass) & 1;
-#pragma unroll 1
-        for (int t = c.grp; t < kTiles; t += kGroups) epi_final_tile<ARCH>(c, pass, t, par);
-    }
+    for (int t = c.grp; t < kTiles; t += kGroups) epi_final_tile<ARCH>(c, t, par);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -478,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char* act = smem;
+    unsigned char* act = smem + smem_act_off;
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + smem_tab_off(ARCH));
     int4* steps = reinterpret_cast<int4*>(smem + smem_step_off(ARCH));
     float* s_bias = reinterpret_cast<float*>(smem + smem_bias_off(ARCH));
@@ -487,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     unsigned int* err = p.flags + 1;
 
     // ---- one-time setup ----------------------------------------------------------------------
-    for (int i = threadIdx.x; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (kFrontPad + kActBytes) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < NS * 32; i += kThreads) s_bias[i] = p.bias[i];
     EpiStep* s_epi = reinterpret_cast<EpiStep*>(smem + smem_epi_off(ARCH));
     if (threadIdx.x < NL - 1) {
@@ -500,24 +539,25 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         e.add = sp.add < 0 ? 0 : (sp.after ? 2 : 1);
         e.add_base = sp.add < 0 ? 0 : skip_c8_base(ARCH, sp.add);
         e.save_base = sp.save < 0 ? -1 : skip_c8_base(ARCH, sp.save);
-        e.pad0 = e.pad1 = 0;
+        e.last = li == NL - 2 ? 1 : 0;
+        e.pad1 = 0;
         s_epi[li] = e;
     }
     if (threadIdx.x == 0) {
         *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kFlagSlot) = 0u;
         *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kNextInSlot) = 0u;
+        *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kIssuedSlot) = 0u;
     }
     for (int s = 0; s < NS; ++s) {
-        const int nu = step_units(ARCH, s), nc = step_chunks(ARCH, s);
+        const int nu = step_units(ARCH, s);
         // Per step kTabStride words: the finished low words of the units' A descriptors (row tile 0,
         // hi planes): start address and the distance to the unit's second K chunk.  Slots behind the
         // last unit repeat unit 0 (they are loaded but never issued).
         for (int u = threadIdx.x; u < kTabStride; u += kThreads) {
             const int uu = u < nu ? u : 0;
-            const int o0 = chunk_off16(ARCH, s, 2 * uu);
-            const int o1 = 2 * uu + 1 < nc ? chunk_off16(ARCH, s, 2 * uu + 1) : o0 + 1;   // dummy chunk: zero weights
-            const uint32_t a16 = (smem_u32(act) >> 4) + kLead + (uint32_t)o0;
-            tab[s * kTabStride + u] = (a16 & 0x3FFFu) | ((uint32_t)(o1 - o0) << 16);
+            // (a conv unit without a second chunk points at the next row: its weights are zero)
+            const uint32_t a16 = (uint32_t)((int)(smem_u32(act) >> 4) + kLead + unit_off16(ARCH, s, uu));
+            tab[s * kTabStride + u] = (a16 & 0x3FFFu) | ((uint32_t)unit_lbo16(ARCH, s, uu) << 16);
         }
         if (threadIdx.x == 0) {
             // B descriptor of unit 0 (unit u is tile16 * u further): steps alternate between the two weight
@@ -537,7 +577,6 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             mbar_init(bars + 8 * (kBarWFree + i), kIssuers);   // every issuing thread commits
         }
         mbar_init(bars + 8 * kBarInReady, kEpiWarps);
-        mbar_init(bars + 8 * kBarConvDone, kIssuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -551,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     const uint32_t tm = s_tmem;
     const long long NB = (p.total_rows + kFB - 1) / kFB;
 
-    if (warp == 0 || warp == 3 || (kIssuers == 3 && warp == 5)) {
+    if (warp == 0 || warp == 3 || (warp >= 5 && warp < kCtrlWarps)) {
         // ================= MMA issue =================
         // kIssuers issuing threads (one elected lane of warps 0, 3 and 5) take the row tiles of the
         // global (step, tile) sequence round robin: the tensor pipe accepts only a couple of
@@ -561,10 +600,11 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         // at different times, and one thread prepares while the others issue.
         // Per step the start-address words of every unit's A and B descriptors are built once into
         // registers (fully unrolled, kMaxUnits slots): issuing a unit is an add and the MMA pair.
-        const int iss = warp == 0 ? 0 : (warp == 3 ? 1 : 2);
+        const int iss = warp == 0 ? 0 : (warp == 3 ? 1 : warp - 3);
         if (elect_one()) {
             const uint32_t flag = bars + 8 * kFlagSlot;
             uint32_t seen = 0;   // last value read from the scout's counter
+            uint32_t issued_seen = 0;   // last value read from the count of tiles whose issue is complete
             uint32_t it = 0;
             for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
                 const bool tr = p.trace != nullptr && blockIdx.x == 0 && it == 1;
@@ -603,6 +643,23 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                             if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
                         }
                         fence_after();
+#if RCED_TC_MAXINFLIGHT > 0
+                        // At most RCED_TC_MAXINFLIGHT tiles are being issued at a time.  Tiles issued concurrently
+                        // share the pipe and finish together; three threads that finish together also prepare
+                        // their next tiles together and the pipe idles meanwhile (a stable mode: it persists
+                        // once entered).  Holding one thread back -- prepared, dependency cleared -- keeps the
+                        // finish times staggered.
+                        {
+                            const uint32_t gidx = k * kTiles + t;   // global tile index
+                            if (gidx >= (uint32_t)RCED_TC_MAXINFLIGHT) {
+                                const uint32_t want = gidx - (uint32_t)RCED_TC_MAXINFLIGHT + 1u;
+                                for (int spin = 0; issued_seen < want; ++spin) {
+                                    issued_seen = ld_acquire(bars + 8 * kIssuedSlot);
+                                    if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
+                                }
+                            }
+                        }
+#endif
                         stamp(p.trace, tr, s, t, 0);
                         const uint32_t d = tm + (uint32_t)(t * kAccCols);
                         const uint32_t toff = 128u * t;   // never carries out of the 14-bit start field
@@ -617,18 +674,31 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                                 }
                             }
                         } else {
-                            // output layer pass: one unit; hi x Whi, lo x Whi, hi x Wlo (rows 48..95 of the tile)
-                            const uint64_t db = make_desc(ub0);
-                            umma_f16(d, make_desc(ua[0] + toff), db, id_a, 0);
-                            umma_f16(d, make_desc(ua[0] + toff + kLo16), db, id_a, 1);
-                            umma_f16(d, make_desc(ua[0] + toff), make_desc(ub0 + (uint32_t)np), id_a, 1);
+                            // output layer: per frame parity (even-frame copy in planes 0-1, odd-frame copy two planes
+                            // further, 32 accumulator columns each) five row-shifted blocks of three products
+#pragma unroll 1
+                            for (int odd = 0; odd < 2; ++odd) {
+                                if (odd && (t == 0 || t == kTiles - 1)) break;   // no odd frame reaches these row tiles
+                                const uint32_t dd = d + (uint32_t)(odd * kFinalN);
+                                const uint32_t po = toff + (uint32_t)(odd * 2 * kPlane16);
+#pragma unroll
+                                for (int u = 0; u < kFinalShifts; ++u) {
+                                    const uint64_t dbh = make_desc(ub0 + (uint32_t)u * tile16);                  // Whi rows 0..31
+                                    const uint64_t dbl = make_desc(ub0 + (uint32_t)u * tile16 + (uint32_t)np);   // Wlo rows 32..63
+                                    umma_f16(dd, make_desc(ua[u] + po), dbh, id_b, u > 0);
+                                    umma_f16(dd, make_desc(ua[u] + po + kLo16), dbh, id_b, 1);
+                                    umma_f16(dd, make_desc(ua[u] + po), dbl, id_b, 1);
+                                }
+                            }
                         }
                         stamp(p.trace, tr, s, t, 7);
                         umma_commit(bars + 8 * (kBarAccFull + t));
+#if RCED_TC_MAXINFLIGHT > 0
+                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(bars + 8 * kIssuedSlot) : "memory");
+#endif
                         stamp(p.trace, tr, s, t, 1);
                     }
                     umma_commit(bars + 8 * (kBarWFree + wb));
-                    if (s == NL - 2) umma_commit(bars + 8 * kBarConvDone);
                 }
             }
         }
@@ -736,7 +806,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         c.grp = (warp - kCtrlWarps) >> 2;   // four consecutive warps cover the four lane quadrants
         c.et = (warp - kCtrlWarps) * 32 + lane;
         c.skip = p.skip + (size_t)blockIdx.x * skip_floats_per_cta(ARCH);
-        c.priv = priv_base(act, warp - kCtrlWarps);
+        c.outp = reinterpret_cast<float*>(smem + smem_out_off(ARCH));
         c.pol_last = l2_policy_evict_last();
         c.pol_first = l2_policy_evict_first();
         float amax = 0.f;
@@ -754,13 +824,6 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             const long long* bn = bnd + (it & 1) * 2 * kFB;
             const float* ib = reinterpret_cast<const float*>(smem + smem_in_off(ARCH)) + (it & 1) * kInRows * kInStride;
             epi_bar();   // every MMA of the previous batch has completed (its epilogues waited)
-            // the output layer's accumulators of the previous batch overlaid planes 2 and 3 (hi),
-            // halo rows included: those must read as zero again before any tap touches them
-            if (it > 0 && c.et < 4 * 16) {
-                const int pl = 2 + ((c.et >> 4) & 1) + (c.et >> 5) * kPlanes, hr = c.et & 15;   // planes 2, 3 of hi and lo
-                const int row = hr < 8 ? hr : kLead + kRows + (hr - 8);
-                reinterpret_cast<uint4*>(act)[pl * kPlane16 + row] = make_uint4(0, 0, 0, 0);
-            }
             // ---- stage the first layer's input: "channel" = time tap, rows g-3 .. g+4 of the utterance
 #pragma unroll 1
             for (int r = c.et; r < kRows; r += 32 * kEpiWarps) {
@@ -787,15 +850,11 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
 
             epi_steps<ARCH>(c, it * NS, amax);
 
-            epi_bar();   // every warp's partial sums of the output layer are complete
-            {
-                for (int i = c.et; i < c.nf * kBins; i += 32 * kEpiWarps) {
-                    const int fi = i / kBins, b = i - fi * kBins;
-                    float acc = 0.f;
-#pragma unroll
-                    for (int w = 0; w < kEpiWarps; ++w) acc += priv_base(act, w)[fi * kFS + b];
-                    st_hint1(p.out + (g0 + fi) * kBins + b, acc + bias_f, c.pol_first);
-                }
+            epi_bar();   // both partial sums of every output row are stored
+            for (int i = c.et; i < c.nf * kBins; i += 32 * kEpiWarps) {
+                const int fi = i / kBins, b = i - fi * kBins;
+                const int row = fi * kFS + b;
+                st_hint1(p.out + (g0 + fi) * kBins + b, (c.outp[row] + c.outp[kRows + row]) + bias_f, c.pol_first);
             }
         }
         // range guard: non-negative floats order like their bit patterns
@@ -842,7 +901,7 @@ void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* b
         uint16_t* base = im + step_w_off(arch, s) / 2;
         for (int u = 0; u < step_units(arch, s); ++u)
             for (int cc = 0; cc < 2; ++cc) {
-                const int ch = 2 * u + cc;
+                const int ch = is_final(arch, s) ? cc : 2 * u + cc;
                 if (ch >= nc) continue;
                 for (int n = 0; n < rows; ++n)
                     for (int e = 0; e < 8; ++e) {
@@ -850,7 +909,8 @@ void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* b
                         const bool want_lo = n >= np;
                         const int nn = want_lo ? n - np : n;
                         if (is_final(arch, s)) {
-                            const int tap = (s - (nl - 1)) * kFinalTaps + nn, ci = 8 * ch + e;
+                            // unit u = block of 32 taps: tap j = 32 u + nn, chunk = channel group
+                            const int tap = u * kFinalN + nn, ci = 8 * cc + e;
                             if (tap < sp.kw && ci < sp.cin) w = k[((size_t)tap * sp.cin + ci) * sp.cout];
                         } else {
                             const int g = ch / sp.kw, j = ch % sp.kw, ci = 8 * g + e;
@@ -869,7 +929,6 @@ void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* b
         else
             for (int o = 0; o < sp.cout; ++o) bias[s * 32 + o] = b[o];
     }
-    // the epilogue role reads the final bias from row NL-1 (the first final pass)
 }
 
 template <int ARCH>

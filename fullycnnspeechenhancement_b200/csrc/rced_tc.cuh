@@ -10,6 +10,14 @@
 // error-compensated split x = hi + lo (two FP16 numbers, 22 significant bits):
 //   x*w ~= hi*Whi + hi*Wlo + lo*Whi     (FP32 accumulation in tensor memory)
 // issued as two instructions per K step: A_hi x [Whi | Wlo] (N = 2*NP) and A_lo x Whi (N = NP).
+//
+// The (1,129) output layer runs "taps in N with row-shifted accumulation": tap j = 32 i + n
+// (i = 0..4, n = 0..31), E[r][n] = sum_i X[r + 32 (i - 2)] . W[32 i + n] -- five MMAs whose A
+// descriptors are shifted by 32 (i - 2) rows accumulate into the same 32 columns -- and
+// out[b] = sum_n E[b + n][n] (a 32-tap diagonal sum in the epilogue instead of a 129-tap one).
+// Rows shifted by up to 64 would reach the neighbouring frame (frame stride 136), therefore the
+// last conv layer writes its output twice, as an "even frames only" copy (planes 0, 1) and an "odd
+// frames only" copy (planes 2, 3, dead by then), and each parity gets its own 32 accumulator columns.
 #pragma once
 #include "rced_arch.cuh"
 
@@ -27,13 +35,15 @@ constexpr int kPlanes = 4;                    // channel groups of 8 (<= 32 chan
 constexpr int kLo16 = kPlanes * kPlane16;     // offset of the lo planes behind the hi planes
 constexpr int kActBytes = 2 * kPlanes * kPlane16 * 16;
 constexpr int kAccCols = 64;                  // tensor-memory columns per tile
-constexpr int kFinalTaps = 48;                // taps of the (1,129) layer per pass (N of the pass)
-constexpr int kFinalPasses = 3;
+constexpr int kFinalN = 32;                   // taps per row-shifted block of the (1,129) layer (N of its instructions)
+constexpr int kFinalShifts = 5;               // blocks: row shifts -64, -32, 0, 32, 64
+constexpr int kFrontRows = 64;                // zero rows in front of plane 0 (the -64 shift of row tile 0 reads them)
+constexpr int kFrontPad = kFrontRows * 16;    // ... in bytes
 #ifndef RCED_TC_ISSUERS
 #define RCED_TC_ISSUERS 3
 #endif
-constexpr int kIssuers = RCED_TC_ISSUERS;     // MMA-issuing threads (2 or 3)
-constexpr int kCtrlWarps = kIssuers == 3 ? 6 : 5;   // warps 0 / 3 / 5: MMA issue (row tiles round robin), 1: weight producer, 2: dependency scout,
+constexpr int kIssuers = RCED_TC_ISSUERS;     // MMA-issuing threads (2 .. 4)
+constexpr int kCtrlWarps = 3 + kIssuers;      // warps 0, 3, 5, 6: MMA issue (row tiles round robin), 1: weight producer, 2: dependency scout,
                                               // 4: prefetch of the next batch's utterance bounds and input rows
 constexpr int kEpiWarps = 16;                 // groups of four warps (one per tensor-memory lane quadrant)
 constexpr int kGroups = kEpiWarps / 4;        // group g takes the row tiles t = g, g + kGroups, ...
@@ -41,17 +51,16 @@ constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
 constexpr int kTraceEvents = 8;               // clock stamps per (step, tile) of the development trace
 constexpr int kInRows = kFB + 7;              // input rows a batch reads: frames g0-3 .. g0+kFB+3
 constexpr int kInStride = 132;                // floats per prefetched input row
-constexpr int kOutStride = 132;               // floats per frame of the output accumulator
 
 static_assert(kFB * kFS <= kRows, "frames of a batch must fit the row tiles");
 static_assert(kFS - kBins >= 6 && kLead >= 6, "zero rows must cover the widest SAME pad (kw = 13)");
 
-// steps: conv layers 0 .. NL-2, then kFinalPasses passes of the (1,129) layer
-RCED_HD constexpr int n_steps(int arch) { return num_layers(arch) - 1 + kFinalPasses; }
+// steps: conv layers 0 .. NL-2, then the (1,129) layer
+RCED_HD constexpr int n_steps(int arch) { return num_layers(arch); }
 RCED_HD constexpr bool is_final(int arch, int s) { return s >= num_layers(arch) - 1; }
 RCED_HD constexpr int step_layer(int arch, int s) { return is_final(arch, s) ? num_layers(arch) - 1 : s; }
 RCED_HD constexpr int step_np(int arch, int s) {
-    return is_final(arch, s) ? kFinalTaps : (spec(arch, s).cout <= 16 ? 16 : 32);
+    return is_final(arch, s) ? kFinalN : (spec(arch, s).cout <= 16 ? 16 : 32);
 }
 RCED_HD constexpr int step_groups(int arch, int s) {
     return is_final(arch, s) ? (spec(arch, num_layers(arch) - 1).cin + 7) / 8 : (cin_eff(arch, s) + 7) / 8;
@@ -59,8 +68,10 @@ RCED_HD constexpr int step_groups(int arch, int s) {
 RCED_HD constexpr int step_chunks(int arch, int s) {
     return is_final(arch, s) ? step_groups(arch, s) : spec(arch, s).kw * step_groups(arch, s);
 }
-RCED_HD constexpr int step_units(int arch, int s) { return (step_chunks(arch, s) + 1) / 2; }
-// B tile of one unit: [2 chunks][rows][8 halfs]; rows = 2*NP (Whi | Wlo), final pass 96 (48 | 48)
+// units: pairs of (tap, group) chunks of a conv layer; the row-shifted blocks of the output layer (whose
+// two chunks are the channel groups, at most 16 channels)
+RCED_HD constexpr int step_units(int arch, int s) { return is_final(arch, s) ? kFinalShifts : (step_chunks(arch, s) + 1) / 2; }
+// B tile of one unit: [2 chunks][rows][8 halfs]; rows = 2*NP (Whi | Wlo)
 RCED_HD constexpr int step_tile_rows(int arch, int s) { return 2 * step_np(arch, s); }
 RCED_HD constexpr int step_tile_bytes(int arch, int s) { return 2 * step_tile_rows(arch, s) * 16; }
 RCED_HD constexpr int step_w_bytes(int arch, int s) { return step_units(arch, s) * step_tile_bytes(arch, s); }
@@ -93,15 +104,29 @@ constexpr int kTabStride = 20;  // words per step in the A-descriptor table (kMa
 static_assert(n_steps(1) % 2 == 0 && n_steps(2) % 2 == 0 && n_steps(3) % 2 == 0, "step s must always use weight buffer s & 1");
 static_assert(max_units(1) <= kMaxUnits && max_units(2) <= kMaxUnits && max_units(3) <= kMaxUnits, "raise kMaxUnits");
 
-// A-operand addressing of chunk c of step s, in 16-byte units relative to row (kLead + 128 t)
+// A-operand addressing of chunk c of conv step s, in 16-byte units relative to row (kLead + 128 t)
 // of plane 0: channel group g = c / kw lives in plane g, tap j = c % kw reads rows shifted by j - pad
 RCED_HD constexpr int chunk_off16(int arch, int s, int c) {
-    if (is_final(arch, s)) return c * kPlane16;
     const int kw = spec(arch, s).kw;
     return (c / kw) * kPlane16 + (c % kw) - (kw - 1) / 2;
 }
+// unit u of step s: offset of its first chunk and distance to its second one.  A conv unit without
+// a second chunk points at the next row (its weights are zero); output-layer unit u is the block
+// shifted by 32 (u - 2) rows, its chunks are the two channel groups (planes 0, 1 of the even-frame
+// copy; the odd-frame copy is 2 planes further)
+RCED_HD constexpr int unit_off16(int arch, int s, int u) {
+    return is_final(arch, s) ? kFinalN * (u - kFinalShifts / 2) : chunk_off16(arch, s, 2 * u);
+}
+RCED_HD constexpr int unit_lbo16(int arch, int s, int u) {
+    if (is_final(arch, s)) return kPlane16;
+    return 2 * u + 1 < step_chunks(arch, s) ? chunk_off16(arch, s, 2 * u + 1) - chunk_off16(arch, s, 2 * u) : 1;
+}
+static_assert(spec(1, num_layers(1) - 1).cin <= 16 && spec(2, num_layers(2) - 1).cin <= 16 && spec(3, num_layers(3) - 1).cin <= 16,
+              "the output layer's input must fit two channel groups");
+static_assert(spec(1, num_layers(1) - 1).kw <= kFinalN * kFinalShifts - kFinalN + 1 && kFinalN * (kFinalShifts / 2) == 64,
+              "tap j = 32 i + n must cover the 129 taps around the centre tap 64");
 
-// ---- skip tensors: FP32 in a per-CTA global scratch, [group of 8 channels][row][8] ----------
+// ---- skip tensors: FP32 in a per-CTA global scratch, [group of 8 channels][half][row][4] ----
 RCED_HD constexpr int skip_c8(int arch, int slot) {
     for (int i = 0; i < num_layers(arch); ++i)
         if (spec(arch, i).save == slot) return (spec(arch, i).cout + 7) / 8;
@@ -117,12 +142,13 @@ RCED_HD constexpr size_t skip_floats_per_cta(int arch) { return (size_t)skip_c8_
 
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------
 RCED_HD constexpr int pad128(int x) { return (x + 127) & ~127; }
-RCED_HD constexpr int smem_w_off(int arch, int buf) { return kActBytes + buf * pad128(max_step_w_bytes(arch)); }
+constexpr int smem_act_off = kFrontPad;   // activation planes, behind the zero rows
+RCED_HD constexpr int smem_w_off(int arch, int buf) { return kFrontPad + kActBytes + buf * pad128(max_step_w_bytes(arch)); }
 RCED_HD constexpr int smem_tab_off(int arch) { return smem_w_off(arch, 2); }                        // uint32[n_steps][kTabStride]
 RCED_HD constexpr int smem_step_off(int arch) { return smem_tab_off(arch) + pad128(4 * kTabStride * n_steps(arch)); }   // int4[n_steps]
 RCED_HD constexpr int smem_bias_off(int arch) { return smem_step_off(arch) + pad128(16 * n_steps(arch)); }     // float[n_steps][32]
-RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 128 * n_steps(arch); }             // float[kFB][kOutStride]
-RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + pad128(4 * kFB * kOutStride); }     // long long[2][kFB][2]
+RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 128 * n_steps(arch); }             // float[2][kRows]: the two partial sums of every output row
+RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + 2 * kRows * 4; }                    // long long[2][kFB][2]
 RCED_HD constexpr int smem_bar_off(int arch) { return smem_bnd_off(arch) + 256; }                              // mbarriers
 RCED_HD constexpr int smem_epi_off(int arch) { return smem_bar_off(arch) + 256; }                             // EpiStep[n_steps]
 RCED_HD constexpr int smem_in_off(int arch) { return smem_epi_off(arch) + pad128(32 * n_steps(arch)); }       // float[2][kInRows][kInStride]
@@ -134,8 +160,8 @@ constexpr int kBarActReady = 8;    // [kTiles]  epilogue of (step, tile) done (p
 constexpr int kBarWFull = 16;      // [2]       weights of a step landed in buffer b
 constexpr int kBarWFree = 18;      // [2]       MMAs reading buffer b complete
 constexpr int kBarInReady = 20;    //           layer-0 input of the batch staged
-constexpr int kBarConvDone = 21;   //           every MMA of the batch's last conv layer complete
 constexpr int kNextInSlot = 25;    //           u32 count of batches whose bounds / input rows the producer has prefetched
+constexpr int kIssuedSlot = 26;    //           u32 count of row tiles whose MMAs have all been issued (and committed)
 constexpr int kFlagSlot = 24;      //           u32 progress counter published by the dependency scout
 
 }  // namespace tc

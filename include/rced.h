@@ -121,9 +121,10 @@ int rced_tc_status(rced_handle* h, float* max_abs, unsigned int* protocol_error)
  * and arithmetic without a GPU.  rced_tc_layout writes: out[0]=steps, [1]=units, [2]=image bytes,
  * [3]=shared-memory bytes, [4]=plane stride (16-byte units), [5]=lead rows, [6]=rows per frame,
  * [7]=frames per batch, [8]=row tiles, [9]=offset of the lo planes (16-byte units), [10]=taps per
- * pass of the output layer, [11]=skip scratch floats per CTA; then per step 6 values (units,
- * first unit, NP, tile bytes, image offset, is_final) and per unit 2 values (start offset and LBO
- * of the A descriptor in 16-byte units).  n >= 12 + 6*steps + 2*units. */
+ * row-shifted block of the output layer, [11]=skip scratch floats per CTA, [12]=row-shifted blocks,
+ * [13]=zero rows in front of plane 0, [14..15]=0; then per step 6 values (units, first unit, NP, tile
+ * bytes, image offset, is_final) and per unit 2 values (start offset and LBO of the A descriptor in
+ * 16-byte units).  n >= 16 + 6*steps + 2*units. */
 int64_t rced_tc_image_bytes(int arch);
 int64_t rced_tc_bias_count(int arch);
 int rced_tc_pack_weights(int arch, const float* folded, size_t n_folded, void* image, size_t image_bytes,

@@ -55,6 +55,13 @@ def test_tc_layout_fits_the_sm():
             for u in range(st["units"]):
                 off, lbo = lay["units"][st["unit_base"] + u]
                 assert lbo > 0
-                assert lay["lead"] + off >= 0
-                assert lay["lead"] + 128 * (lay["tiles"] - 1) + off + lbo + 128 <= 4 * lay["plane16"]
+                assert lay["front_rows"] + lay["lead"] + off >= 0            # the -64-row shift reads the zero front rows
+                if not st["final"]:
+                    assert lay["lead"] + 128 * (lay["tiles"] - 1) + off + lbo + 128 <= 4 * lay["plane16"]
+                else:   # even-frame copy in planes 0-1; the +64 shift of the last row tile ends in the next plane's lead rows
+                    assert lbo == lay["plane16"] and abs(off) <= 64
+                    # the last E row any output needs is bin 128 of the last frame + 31 columns: its shifted read
+                    # must end inside the zero lead rows of the next plane (rows behind it feed no output)
+                    last_needed = (lay["fb"] - 1) * lay["fs"] + 128 + lay["final_n"] - 1
+                    assert lay["lead"] + last_needed + off < lay["plane16"] + lay["lead"]
             assert st["tile_bytes"] % 16 == 0 and st["w_off"] % 16 == 0

@@ -5,7 +5,9 @@ weight image and bias table produced by rced_tc_pack_weights, the per-unit A-des
 rced_tc_layout (start offset and leading-dimension offset in 16-byte units, rows linear at 16
 bytes), the flattened (frame, bin) row space with its zero halo rows, in-place plane updates,
 the two instructions per K step (A_hi x [Whi | Wlo], A_lo x Whi) with FP32 accumulation, the
-"taps in N" passes of the (1,129) layer with the same-frame mask, and the FP32 skip scratch.
+even / odd frame copies written by the last conv layer, the row-shifted blocks of the (1,129) layer
+(reads before plane 0 land in the zero front rows) with its 32-column diagonal sums, and the FP32
+skip scratch.
 It needs no GPU, only the host functions of librced_b200.so; tests/test_tc_cpu.py compares it
 with the float64 oracle, which pins both the layout and the accuracy of the FP16 x3 split.
 """
@@ -21,11 +23,12 @@ def layout(lib, arch):
     assert lib.rced_tc_layout(arch, out, len(out)) == 0, lib.rced_last_error()
     ns, nu = out[0], out[1]
     lay = dict(ns=ns, nu=nu, image_bytes=out[2], smem=out[3], plane16=out[4], lead=out[5], fs=out[6], fb=out[7],
-               tiles=out[8], lo16=out[9], final_taps=out[10], skip_floats=out[11], steps=[], units=[])
+               tiles=out[8], lo16=out[9], final_n=out[10], skip_floats=out[11], final_shifts=out[12], front_rows=out[13],
+               steps=[], units=[])
     for s in range(ns):
-        o = out[12 + 6 * s: 18 + 6 * s]
+        o = out[16 + 6 * s: 22 + 6 * s]
         lay["steps"].append(dict(units=o[0], unit_base=o[1], np=o[2], tile_bytes=o[3], w_off=o[4], final=bool(o[5])))
-    u0 = 12 + 6 * ns
+    u0 = 16 + 6 * ns
     lay["units"] = [(out[u0 + 2 * i], out[u0 + 2 * i + 1]) for i in range(nu)]
     return lay
 
@@ -71,8 +74,11 @@ def run(lib, arch, folded, mag, row_off, table):
     for g0 in range(0, total, FB):
         nf = min(FB, total - g0)
         valid = (fi_of < nf) & (b_of < BINS)
-        # flat[16-byte unit][8 halfs]: hi planes then lo planes, like the shared-memory array
-        flat = np.zeros((2 * LO16, 8), np.float16)
+        # flat[16-byte unit][8 halfs]: zero front rows, hi planes, lo planes, like the shared-memory array (FR: index
+        # of plane 0's first unit); what follows the lo planes in shared memory (the weight buffer) is finite garbage
+        FR = lay["front_rows"]
+        flat = np.zeros((FR + 2 * LO16 + 128, 8), np.float16)
+        flat[FR + 2 * LO16:] = 3.0
         # ---- staging of the first layer's input ("channel" = time tap)
         v = np.zeros((ROWS, 8), np.float32)
         for fi in range(nf):
@@ -85,42 +91,45 @@ def run(lib, arch, folded, mag, row_off, table):
                     v[fi * FS: fi * FS + BINS, tt] = mag[src]
         amax = max(amax, float(np.abs(v).max()))
         h, l = split(v)
-        flat[LEAD: LEAD + ROWS] = h
-        flat[LO16 + LEAD: LO16 + LEAD + ROWS] = l
+        flat[FR + LEAD: FR + LEAD + ROWS] = h
+        flat[FR + LO16 + LEAD: FR + LO16 + LEAD + ROWS] = l
         saved = {}
-        outrow = np.zeros(ROWS, np.float32)
+        outp = np.full((2, ROWS), np.nan, np.float32)
         for s, st in enumerate(lay["steps"]):
             NP = st["np"]
             rows_b = 2 * NP
             tile_h = st["tile_bytes"] // 2
             D = np.zeros((ROWS, 64), np.float32)
             for t in range(TILES):
+                sl = slice(128 * t, 128 * t + 128)
                 for u in range(st["units"]):
                     off16, lbo16 = lay["units"][st["unit_base"] + u]
-                    start = LEAD + 128 * t + off16
-                    a_hi = np.concatenate([flat[start: start + 128], flat[start + lbo16: start + lbo16 + 128]], axis=1)
-                    a_lo = np.concatenate([flat[LO16 + start: LO16 + start + 128],
-                                           flat[LO16 + start + lbo16: LO16 + start + lbo16 + 128]], axis=1)
                     tile = halfs[st["w_off"] // 2 + u * tile_h: st["w_off"] // 2 + (u + 1) * tile_h].reshape(2, rows_b, 8)
                     B = np.concatenate([tile[0], tile[1]], axis=1).astype(np.float32)   # [rows_b][16]
-                    a_hi = a_hi.astype(np.float32)
-                    a_lo = a_lo.astype(np.float32)
-                    sl = slice(128 * t, 128 * t + 128)
-                    if not st["final"]:
-                        pa = a_hi @ B.T
-                        if u == 0:
-                            D[sl, :rows_b] = pa
+                    for odd in range(2 if st["final"] else 1):
+                        if odd and t in (0, TILES - 1):
+                            continue
+                        start = FR + LEAD + 128 * t + off16 + odd * 2 * P16
+                        a_hi = np.concatenate([flat[start: start + 128], flat[start + lbo16: start + lbo16 + 128]],
+                                              axis=1).astype(np.float32)
+                        a_lo = np.concatenate([flat[LO16 + start: LO16 + start + 128],
+                                               flat[LO16 + start + lbo16: LO16 + start + lbo16 + 128]], axis=1).astype(np.float32)
+                        if not st["final"]:
+                            pa = a_hi @ B.T
+                            if u == 0:
+                                D[sl, :rows_b] = pa
+                            else:
+                                D[sl, :rows_b] += pa
+                            D[sl, :NP] += a_lo @ B[:NP].T
                         else:
-                            D[sl, :rows_b] += pa
-                        D[sl, :NP] += a_lo @ B[:NP].T
-                    else:
-                        pa = a_hi @ B[:NP].T
-                        if u == 0:
-                            D[sl, :NP] = pa
-                        else:
-                            D[sl, :NP] += pa
-                        D[sl, :NP] += a_lo @ B[:NP].T
-                        D[sl, :NP] += a_hi @ B[NP:].T
+                            c0 = odd * NP
+                            pa = a_hi @ B[:NP].T
+                            if u == 0:
+                                D[sl, c0:c0 + NP] = pa
+                            else:
+                                D[sl, c0:c0 + NP] += pa
+                            D[sl, c0:c0 + NP] += a_lo @ B[:NP].T
+                            D[sl, c0:c0 + NP] += a_hi @ B[NP:].T
             if not st["final"]:
                 L = table[s]
                 cout = L["cout"]
@@ -136,18 +145,45 @@ def run(lib, arch, folded, mag, row_off, table):
                 amax = max(amax, float(np.abs(x).max()))
                 saved[scopes[s]] = x
                 h, l = split(x)
+                last = s == nl - 2
+                odd_row = (fi_of % 2 == 1)[:, None]
                 for g in range(cg):
-                    flat[g * P16 + LEAD: g * P16 + LEAD + ROWS] = h[:, 8 * g: 8 * g + 8]
-                    flat[LO16 + g * P16 + LEAD: LO16 + g * P16 + LEAD + ROWS] = l[:, 8 * g: 8 * g + 8]
+                    hg, lg = h[:, 8 * g: 8 * g + 8], l[:, 8 * g: 8 * g + 8]
+                    if not last:
+                        flat[FR + g * P16 + LEAD: FR + g * P16 + LEAD + ROWS] = hg
+                        flat[FR + LO16 + g * P16 + LEAD: FR + LO16 + g * P16 + LEAD + ROWS] = lg
+                    else:   # even-frame copy in planes g, odd-frame copy in planes g + 2, zeros in the other one
+                        z = np.zeros_like(hg)
+                        flat[FR + g * P16 + LEAD: FR + g * P16 + LEAD + ROWS] = np.where(odd_row, z, hg)
+                        flat[FR + LO16 + g * P16 + LEAD: FR + LO16 + g * P16 + LEAD + ROWS] = np.where(odd_row, z, lg)
+                        flat[FR + (g + 2) * P16 + LEAD: FR + (g + 2) * P16 + LEAD + ROWS] = np.where(odd_row, hg, z)
+                        flat[FR + LO16 + (g + 2) * P16 + LEAD: FR + LO16 + (g + 2) * P16 + LEAD + ROWS] = np.where(odd_row, lg, z)
             else:
-                p = s - (nl - 1)
-                for i in range(lay["final_taps"]):
-                    tap = p * lay["final_taps"] + i
-                    ob = b_of - tap + 64
-                    m = valid & (ob >= 0) & (ob < BINS)
-                    ro = r_idx - tap + 64
-                    np.add.at(outrow, ro[m], D[m, i])
+                # E[r][n] belongs to output row r - n; per 32-row block the diagonal sums are split into the part that
+                # stays in the block (outp[0]) and the part that falls into the previous block (outp[1]); a sum is
+                # stored only on a valid row of a frame of the accumulator's parity
+                for t in range(TILES):
+                    for q in range(4):
+                        r0 = 128 * t + 32 * q
+                        for odd in range(2):
+                            if odd and t in (0, TILES - 1):
+                                continue
+                            own = np.zeros(32, np.float32)
+                            prev = np.zeros(32, np.float32)
+                            for n in range(NP):
+                                for lane in range(32):
+                                    d = lane - n
+                                    if d >= 0:
+                                        own[d] += D[r0 + lane, odd * NP + n]
+                                    else:
+                                        prev[d + 32] += D[r0 + lane, odd * NP + n]
+                            for m in range(32):
+                                ra, rb = r0 + m, r0 + m - 32
+                                if valid[ra] and fi_of[ra] % 2 == odd:
+                                    outp[0, ra] = own[m]
+                                if rb >= 0 and valid[rb] and fi_of[rb] % 2 == odd:
+                                    outp[1, rb] = prev[m]
         bias_f = bias[(nl - 1) * 32]
         for fi in range(nf):
-            pred[g0 + fi] = outrow[fi * FS: fi * FS + BINS] + bias_f
+            pred[g0 + fi] = (outp[0, fi * FS: fi * FS + BINS] + outp[1, fi * FS: fi * FS + BINS]) + bias_f
     return pred, amax
