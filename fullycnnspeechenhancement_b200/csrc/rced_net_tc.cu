@@ -279,6 +279,31 @@ __device__ __forceinline__ void store_split8_parity(unsigned char* act, int cg, 
     po[kLo16] = odd ? l : z;
 }
 
+// Per-step issue parameters and the units' A-descriptor words in CONSTANT memory: the issuing thread
+// indexes them with warp-uniform loop counters, so the loads and all descriptor arithmetic run in the
+// uniform datapath (LDCU / UIADD3) and land in the uniform registers tcgen05.mma takes its operands
+// from -- no per-unit R2UR moves, no per-step prologue.  a[s][u] = (LBO << 16) + first-chunk offset in
+// 16-byte units relative to row kLead of plane 0 (may be negative: the sum with the plane address is not).
+template <int ARCH>
+struct IssueTab {
+    int a[n_steps(ARCH) * kTabStride];
+    int nu[n_steps(ARCH)], np[n_steps(ARCH)], tile16[n_steps(ARCH)], rows[n_steps(ARCH)];
+    constexpr IssueTab() : a{}, nu{}, np{}, tile16{}, rows{} {
+        for (int s = 0; s < n_steps(ARCH); ++s) {
+            nu[s] = step_units(ARCH, s);
+            np[s] = step_np(ARCH, s);
+            tile16[s] = step_tile_bytes(ARCH, s) >> 4;
+            rows[s] = step_tile_rows(ARCH, s);
+            for (int u = 0; u < kTabStride; ++u) {
+                const int uu = u < step_units(ARCH, s) ? u : 0;
+                a[s * kTabStride + u] = unit_lbo16(ARCH, s, uu) * 65536 + kLead + unit_off16(ARCH, s, uu);
+            }
+        }
+    }
+};
+template <int ARCH>
+__constant__ IssueTab<ARCH> c_issue = IssueTab<ARCH>();
+
 struct TcParams {
     const unsigned char* wimg;   // weight image (global): per step, per unit, [2][rows][8] halfs
     const float* bias;           // [n_steps][32]
@@ -516,10 +541,8 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     __shared__ uint32_t s_tmem;
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler (uniform datapath)
     unsigned char* act = smem + smem_act_off;
-    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + smem_tab_off(ARCH));
-    int4* steps = reinterpret_cast<int4*>(smem + smem_step_off(ARCH));
     float* s_bias = reinterpret_cast<float*>(smem + smem_bias_off(ARCH));
     long long* bnd = reinterpret_cast<long long*>(smem + smem_bnd_off(ARCH));
     const uint32_t bars = smem_u32(smem + smem_bar_off(ARCH));
@@ -547,25 +570,6 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kFlagSlot) = 0u;
         *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kNextInSlot) = 0u;
         *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kIssuedSlot) = 0u;
-    }
-    for (int s = 0; s < NS; ++s) {
-        const int nu = step_units(ARCH, s);
-        // Per step kTabStride words: the finished low words of the units' A descriptors (row tile 0,
-        // hi planes): start address and the distance to the unit's second K chunk.  Slots behind the
-        // last unit repeat unit 0 (they are loaded but never issued).
-        for (int u = threadIdx.x; u < kTabStride; u += kThreads) {
-            const int uu = u < nu ? u : 0;
-            // (a conv unit without a second chunk points at the next row: its weights are zero)
-            const uint32_t a16 = (uint32_t)((int)(smem_u32(act) >> 4) + kLead + unit_off16(ARCH, s, uu));
-            tab[s * kTabStride + u] = (a16 & 0x3FFFu) | ((uint32_t)unit_lbo16(ARCH, s, uu) << 16);
-        }
-        if (threadIdx.x == 0) {
-            // B descriptor of unit 0 (unit u is tile16 * u further): steps alternate between the two weight
-            // buffers and n_steps is even, so step s always uses buffer s & 1
-            const uint32_t w16 = smem_u32(smem + smem_w_off(ARCH, s & 1)) >> 4;
-            steps[s] = make_int4(nu, (int)((w16 & 0x3FFFu) | ((uint32_t)step_tile_rows(ARCH, s) << 16)), step_np(ARCH, s),
-                                 (step_tile_bytes(ARCH, s) >> 4) | (is_final(ARCH, s) ? (1 << 16) : 0));
-        }
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTiles; ++i) {
@@ -605,6 +609,9 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             const uint32_t flag = bars + 8 * kFlagSlot;
             uint32_t seen = 0;   // last value read from the scout's counter
             uint32_t issued_seen = 0;   // last value read from the count of tiles whose issue is complete
+            const uint32_t a16_0 = smem_u32(act) >> 4;                                   // plane 0, in 16-byte units
+            const uint32_t w16_0 = smem_u32(smem + smem_w_off(ARCH, 0)) >> 4;            // weight buffer 0
+            const uint32_t w16_step = (uint32_t)(smem_w_off(ARCH, 1) - smem_w_off(ARCH, 0)) >> 4;
             uint32_t it = 0;
             for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
                 const bool tr = p.trace != nullptr && blockIdx.x == 0 && it == 1;
@@ -612,24 +619,14 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 for (int s = 0; s < NS; ++s) {
                     const uint32_t k = it * NS + s;
                     const int wb = k & 1;
-                    const int4 st = steps[s];
-                    const int nu = st.x, np = st.z;
-                    const bool fin = (st.w >> 16) != 0;
+                    const int nu = c_issue<ARCH>.nu[s], np = c_issue<ARCH>.np[s];
+                    const bool fin = s == NL - 1;
                     const uint32_t id_a = idesc_f16(fin ? np : 2 * np), id_b = idesc_f16(np);
-                    uint32_t ua[kMaxUnits];   // A descriptor low words, built at kernel start: five 16-byte loads
-                    {
-                        const uint4* ut = reinterpret_cast<const uint4*>(tab + s * kTabStride);
-#pragma unroll
-                        for (int q = 0; q < kTabStride / 4; ++q) {
-                            const uint4 w = ut[q];
-                            if (4 * q + 0 < kMaxUnits) ua[4 * q + 0] = w.x;
-                            if (4 * q + 1 < kMaxUnits) ua[4 * q + 1] = w.y;
-                            if (4 * q + 2 < kMaxUnits) ua[4 * q + 2] = w.z;
-                            if (4 * q + 3 < kMaxUnits) ua[4 * q + 3] = w.w;
-                        }
-                    }
-                    const uint32_t ub0 = (uint32_t)st.y;             // B descriptor of unit 0; unit u is tile16 * u further
-                    const uint32_t tile16 = (uint32_t)(st.w & 0xFFFF);
+                    const int* ta = c_issue<ARCH>.a + s * kTabStride;
+                    // B descriptor of unit 0 (unit u is tile16 * u further): steps alternate between the two weight
+                    // buffers and n_steps is even, so step s always uses buffer s & 1
+                    const uint32_t tile16 = (uint32_t)c_issue<ARCH>.tile16[s];
+                    const uint32_t ub0 = ((w16_0 + (uint32_t)(s & 1) * w16_step) & 0x3FFFu) | ((uint32_t)c_issue<ARCH>.rows[s] << 16);
                     const int t_first = (iss + kIssuers - (int)((k * kTiles) % kIssuers)) % kIssuers;
 #pragma unroll 1
                     for (int t = t_first; t < kTiles; t += kIssuers) {
@@ -664,14 +661,13 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                         const uint32_t d = tm + (uint32_t)(t * kAccCols);
                         const uint32_t toff = 128u * t;   // never carries out of the 14-bit start field
                         if (!fin) {
-#pragma unroll
-                            for (int u = 0; u < kMaxUnits; ++u) {
-                                if (u < nu) {
-                                    const uint64_t db = make_desc(ub0 + (uint32_t)u * tile16);
-                                    umma_f16(d, make_desc(ua[u] + toff), db, id_a, u > 0);     // hi x [Whi | Wlo] -> columns [0, 2 NP)
-                                    umma_f16(d, make_desc(ua[u] + toff + kLo16), db, id_b, 1); // lo x Whi        -> columns [0, NP)
-                                    if (u == 0) stamp(p.trace, tr, s, t, 6);
-                                }
+#pragma unroll 2
+                            for (int u = 0; u < nu; ++u) {
+                                const uint32_t ua = a16_0 + (uint32_t)ta[u] + toff;
+                                const uint64_t db = make_desc(ub0 + (uint32_t)u * tile16);
+                                umma_f16(d, make_desc(ua), db, id_a, u > 0);     // hi x [Whi | Wlo] -> columns [0, 2 NP)
+                                umma_f16(d, make_desc(ua + kLo16), db, id_b, 1); // lo x Whi        -> columns [0, NP)
+                                if (u == 0) stamp(p.trace, tr, s, t, 6);
                             }
                         } else {
                             // output layer: per frame parity (even-frame copy in planes 0-1, odd-frame copy two planes
@@ -685,9 +681,10 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                                 for (int u = 0; u < kFinalShifts; ++u) {
                                     const uint64_t dbh = make_desc(ub0 + (uint32_t)u * tile16);                  // Whi rows 0..31
                                     const uint64_t dbl = make_desc(ub0 + (uint32_t)u * tile16 + (uint32_t)np);   // Wlo rows 32..63
-                                    umma_f16(dd, make_desc(ua[u] + po), dbh, id_b, u > 0);
-                                    umma_f16(dd, make_desc(ua[u] + po + kLo16), dbh, id_b, 1);
-                                    umma_f16(dd, make_desc(ua[u] + po), dbl, id_b, 1);
+                                    const uint32_t ua = a16_0 + (uint32_t)ta[u] + po;
+                                    umma_f16(dd, make_desc(ua), dbh, id_b, u > 0);
+                                    umma_f16(dd, make_desc(ua + kLo16), dbh, id_b, 1);
+                                    umma_f16(dd, make_desc(ua), dbl, id_b, 1);
                                 }
                             }
                         }
