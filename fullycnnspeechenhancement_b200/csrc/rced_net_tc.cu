@@ -515,21 +515,6 @@ __device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const 
     stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 4);
 }
 
-// all steps of one batch for this epilogue warp
-template <int ARCH>
-__device__ __forceinline__ void epi_steps(const Ctx& c, const uint32_t k0, float& amax) {
-    constexpr int NL = num_layers(ARCH);
-#pragma unroll 1
-    for (int s = 0; s < NL - 1; ++s) {
-        const uint32_t par = (k0 + s) & 1;
-#pragma unroll 1
-        for (int t = c.grp; t < kTiles; t += kGroups) epi_conv_tile(c, s, t, par, amax);
-    }
-    const uint32_t par = (k0 + NL - 1) & 1;
-#pragma unroll 1
-    for (int t = c.grp; t < kTiles; t += kGroups) epi_final_tile<ARCH>(c, t, par);
-}
-
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
@@ -581,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             mbar_init(bars + 8 * (kBarWFree + i), kIssuers);   // every issuing thread commits
         }
         mbar_init(bars + 8 * kBarInReady, kEpiWarps);
+        mbar_init(bars + 8 * kBarFinalDone, kIssuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -696,6 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                         stamp(p.trace, tr, s, t, 1);
                     }
                     umma_commit(bars + 8 * (kBarWFree + wb));
+                    if (s == NL - 1) umma_commit(bars + 8 * kBarFinalDone);   // the planes are free for the next batch's input
                 }
             }
         }
@@ -729,6 +716,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         float* inbuf = reinterpret_cast<float*>(smem + smem_in_off(ARCH));
         const uint32_t flag = bars + 8 * kFlagSlot;
         uint32_t itn = 0;   // local index of the batch being prefetched
+        float in_amax = 0.f;
         for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++itn) {
             if (itn >= 2) {
                 // buffer itn & 1 was read by the staging of batch itn - 2: wait until the scout has
@@ -740,24 +728,35 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 }
             }
             const long long g0 = batch * kFB;
-            long long* bn = bnd + (itn & 1) * 2 * kFB;
+            // per frame of the batch: which of its 8 time taps (rows g-3 .. g+4) lie inside its utterance
+            int* tm8 = reinterpret_cast<int*>(bnd) + (itn & 1) * 8;
             if (lane < kFB) {
                 long long lo = 0, hi = 0;
-                if (g0 + lane < p.total_rows) locate(p.row_off, p.n_utt, g0 + lane, lo, hi);
-                bn[2 * lane] = lo;
-                bn[2 * lane + 1] = hi;
+                const long long g = g0 + lane;
+                if (g < p.total_rows) locate(p.row_off, p.n_utt, g, lo, hi);
+                int m = 0;
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt) m |= (g + tt - 3 >= lo && g + tt - 3 < hi) ? (1 << tt) : 0;
+                tm8[lane] = m;
             }
             float* ib = inbuf + (itn & 1) * kInRows * kInStride;
             for (int j = 0; j < kInRows; ++j) {
                 const long long src = g0 - 3 + j;
                 const bool ok = src >= 0 && src < p.total_rows;
-                for (int b = lane; b < kBins; b += 32) ib[j * kInStride + b] = ok ? __ldg(p.in + src * kBins + b) : 0.f;
+                for (int b = lane; b < kBins; b += 32) {
+                    const float x = ok ? __ldg(p.in + src * kBins + b) : 0.f;
+                    in_amax = fmaxf(in_amax, fabsf(x));   // range guard of the first layer's input
+                    ib[j * kInStride + b] = x;
+                }
             }
             __syncwarp();
             // a counter, not an mbarrier: this warp may be two batches ahead of the epilogue warps,
             // which a phase parity could not tell apart
             if (lane == 0) st_release(bars + 8 * kNextInSlot, itn + 1);
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) in_amax = fmaxf(in_amax, __shfl_xor_sync(0xffffffffu, in_amax, d));
+        if (lane == 0) atomicMax(p.flags, __float_as_uint(in_amax));
     } else if (warp == 2) {
         // ================= dependency scout =================
         // Waits, in the MMA thread's issue order, on the mbarriers every (step, tile) depends on and
@@ -776,9 +775,10 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                         if (t == 0) {
                             if (s == 0) mbar_wait(bars + 8 * kBarInReady, it & 1, err, 1);
                             mbar_wait(bars + 8 * (kBarWFull + wb), (k >> 1) & 1, err, 2);
-                            if (s > 0) mbar_wait(bars + 8 * (kBarActReady + 0), (k - 1) & 1, err, 3);
+                            if (k > 0) mbar_wait(bars + 8 * (kBarActReady + 0), (k - 1) & 1, err, 3);
                         }
-                        if (s > 0 && t + 1 < kTiles) mbar_wait(bars + 8 * (kBarActReady + t + 1), (k - 1) & 1, err, 4);
+                        // (step 0 of a batch: the output layer's epilogues of the batch before have read the accumulators)
+                        if (k > 0 && t + 1 < kTiles) mbar_wait(bars + 8 * (kBarActReady + t + 1), (k - 1) & 1, err, 4);
                         st_release(flag, ++done);
                     }
                 }
@@ -808,33 +808,24 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         c.pol_first = l2_policy_evict_first();
         float amax = 0.f;
         const float bias_f = s_bias[(NL - 1) * 32];
-        uint32_t it = 0;
-        for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
-            const long long g0 = batch * kFB;
-            const long long left = p.total_rows - g0;
-            c.nf = left < kFB ? (int)left : kFB;
-            c.g0 = g0;
-            c.tracing = p.trace != nullptr && blockIdx.x == 0 && it == 1;
-            // bounds and input rows of this batch were prefetched by the producer warp
-            for (int spin = 0; ld_acquire(bars + 8 * kNextInSlot) <= it; ++spin)
+        // Stages the first layer's input of batch sb (local index sit): "channel" = time tap, rows g-3 .. g+4
+        // of the utterance, from the block the prefetch warp has loaded.  Plane 0 must be free.
+        auto stage_input = [&](const long long sb, const uint32_t sit) {
+            const long long sg0 = sb * kFB;
+            const long long left = p.total_rows - sg0;
+            const int snf = left < kFB ? (int)left : kFB;
+            for (int spin = 0; ld_acquire(bars + 8 * kNextInSlot) <= sit; ++spin)
                 if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
-            const long long* bn = bnd + (it & 1) * 2 * kFB;
-            const float* ib = reinterpret_cast<const float*>(smem + smem_in_off(ARCH)) + (it & 1) * kInRows * kInStride;
-            epi_bar();   // every MMA of the previous batch has completed (its epilogues waited)
-            // ---- stage the first layer's input: "channel" = time tap, rows g-3 .. g+4 of the utterance
+            const int* tm8 = reinterpret_cast<const int*>(bnd) + (sit & 1) * 8;
+            const float* ib = reinterpret_cast<const float*>(smem + smem_in_off(ARCH)) + (sit & 1) * kInRows * kInStride;
 #pragma unroll 1
             for (int r = c.et; r < kRows; r += 32 * kEpiWarps) {
                 const int fi = r / kFS, b = r - fi * kFS;
                 float v[8];
-                if (fi < c.nf && b < kBins) {
-                    const long long lo = bn[2 * fi], hi = bn[2 * fi + 1];
-                    const long long g = g0 + fi;
+                if (fi < snf && b < kBins) {
+                    const int m = tm8[fi];
 #pragma unroll
-                    for (int tt = 0; tt < 8; ++tt) {
-                        const long long src = g + tt - 3;   // input row fi + tt of the prefetched block
-                        v[tt] = (src >= lo && src < hi) ? ib[(fi + tt) * kInStride + b] : 0.f;
-                        amax = fmaxf(amax, fabsf(v[tt]));
-                    }
+                    for (int tt = 0; tt < 8; ++tt) v[tt] = (m >> tt) & 1 ? ib[(fi + tt) * kInStride + b] : 0.f;   // input row fi + tt of the block
                 } else {
 #pragma unroll
                     for (int tt = 0; tt < 8; ++tt) v[tt] = 0.f;
@@ -844,9 +835,36 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + 8 * kBarInReady);
-
-            epi_steps<ARCH>(c, it * NS, amax);
-
+        };
+        if ((long long)blockIdx.x < NB) stage_input(blockIdx.x, 0);
+        uint32_t it = 0;
+        for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
+            const long long g0 = batch * kFB;
+            const long long left = p.total_rows - g0;
+            c.nf = left < kFB ? (int)left : kFB;
+            c.g0 = g0;
+            c.tracing = p.trace != nullptr && blockIdx.x == 0 && it == 1;
+            const uint32_t k0 = it * NS;
+#pragma unroll 1
+            for (int s = 0; s < NL - 1; ++s) {
+                const uint32_t par = (k0 + s) & 1;
+#pragma unroll 1
+                for (int t = c.grp; t < kTiles; t += kGroups) epi_conv_tile(c, s, t, par, amax);
+            }
+            // Output layer.  Between this warp's two row tiles the next batch's input is staged: plane 0 is
+            // free as soon as the output layer's MMAs have completed, so the first layer of the next
+            // batch starts on the row tiles whose accumulators have been read while the epilogues of the
+            // later ones still run (the scout holds every tile back until its accumulator is free).
+            {
+                const uint32_t par = (k0 + NL - 1) & 1;
+                static_assert(kTiles == 2 * kGroups, "two row tiles per epilogue group");
+                epi_final_tile<ARCH>(c, c.grp, par);
+                if (batch + gridDim.x < NB) {
+                    mbar_wait(bars + 8 * kBarFinalDone, it & 1, err, 6);
+                    stage_input(batch + gridDim.x, it + 1);
+                }
+                epi_final_tile<ARCH>(c, c.grp + kGroups, par);
+            }
             epi_bar();   // both partial sums of every output row are stored
             for (int i = c.et; i < c.nf * kBins; i += 32 * kEpiWarps) {
                 const int fi = i / kBins, b = i - fi * kBins;

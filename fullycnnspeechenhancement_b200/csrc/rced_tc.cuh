@@ -160,6 +160,7 @@ constexpr int kBarActReady = 8;    // [kTiles]  epilogue of (step, tile) done (p
 constexpr int kBarWFull = 16;      // [2]       weights of a step landed in buffer b
 constexpr int kBarWFree = 18;      // [2]       MMAs reading buffer b complete
 constexpr int kBarInReady = 20;    //           layer-0 input of the batch staged
+constexpr int kBarFinalDone = 21;  //           every MMA of the batch's output layer complete (plane 0 may be overwritten)
 constexpr int kNextInSlot = 25;    //           u32 count of batches whose bounds / input rows the producer has prefetched
 constexpr int kIssuedSlot = 26;    //           u32 count of row tiles whose MMAs have all been issued (and committed)
 constexpr int kFlagSlot = 24;      //           u32 progress counter published by the dependency scout
