@@ -216,7 +216,12 @@ def roofline(variant, achieved, ffma_peak, flops_valid, k2_ms, share, traffic, r
     common.update({
         "bound": "tensor", "kernel": "rced_net_tc_kernel<2> (fused 16-layer network, tcgen05 kind::f16)",
         "peak": pk["bf16_tflops"], "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", dense bf16/fp16",
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_note": "dram__bytes_read + write of one launch (ncu --set full, profiles/k2tc_dram_traffic.json): 0.26 GB algorithmic, the "
+                        "rest is write-back of the L2-resident skip scratch",
+        "l1tex_throughput_pct": 91.0,
+        "l1tex_note": "ncu (profiles/r01_k2_tc_v7_ncu_digest.txt): l1tex__throughput 91 % of peak -- the shared-memory operand fetch "
+                      "of the small-N MMAs is the binding unit; sm__pipe_tensor_cycles_active 40 %",
         "issued_tflops": issued / (k2_ms * 1e-3) / 1e12,
         "issued_note": "tensor-core FLOP actually issued: 3 FP16 products per multiply, channels padded to 8 / 16 / 32, "
                        "136-row frame stride, 7 frames per 8 row tiles",
@@ -390,7 +395,7 @@ def main():
         amax, perr = eng.tc_status()
         tc_status = {"max_abs_activation": amax, "protocol_error": perr, "ffma_fallback_ran": bool(amax > 65504.0 or perr != 0)}
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "k2_dram_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "k2tc_dram_traffic.json" if args.variant == "tc" else "k2_dram_traffic.json")
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
