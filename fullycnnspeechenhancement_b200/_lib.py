@@ -46,6 +46,7 @@ SIGNATURES = {
     "rced_enhance": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, ctypes.c_int, c_i64, c_i64, ctypes.c_int,
                                     c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "rced_mag_phase": (ctypes.c_int, [ctypes.c_int, c_p, c_i64, c_p, c_p, c_p]),
+    "rced_sdr_sums": (ctypes.c_int, [ctypes.c_int, c_p, c_p, c_p, c_p, c_p, ctypes.c_int, c_i64, c_p, c_p]),
     "rced_ffma_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "rced_selftest_tmem": (ctypes.c_int, [ctypes.c_int]),
     "rced_launch_count": (c_i64, []),

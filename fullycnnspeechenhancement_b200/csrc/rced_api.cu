@@ -78,6 +78,43 @@ cudaError_t run_ffma_peak(int iters, int num_sms, double* tflops) {
     return e;
 }
 
+// ---- energy sums of the SDR score (model_utils/utils.py:68-78 of the reference) --------------------
+// One CTA per (utterance, chunk): float64 sums of ref^2 and (est - ref)^2, a warp-shuffle tree inside
+// the CTA, one atomic pair per CTA.  sums[u] = {sum ref^2, sum (est - ref)^2}.
+__global__ void __launch_bounds__(256) sdr_sums_kernel(const float* __restrict__ ref, const float* __restrict__ est,
+                                                       const long long* __restrict__ off_ref, const long long* __restrict__ off_est,
+                                                       const int* __restrict__ len, double* __restrict__ sums) {
+    const int u = blockIdx.y;
+    const long long n = len[u];
+    const float* r = ref + off_ref[u];
+    const float* e = est + off_est[u];
+    double a = 0.0, b = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double y = (double)__ldg(r + i), d = (double)__ldg(e + i) - y;
+        a += y * y;
+        b += d * d;
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, k);
+        b += __shfl_xor_sync(0xffffffffu, b, k);
+    }
+    __shared__ double sa[8], sb[8];
+    if ((threadIdx.x & 31) == 0) {
+        sa[threadIdx.x >> 5] = a;
+        sb[threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            a += sa[w];
+            b += sb[w];
+        }
+        atomicAdd(sums + 2 * u, a);
+        atomicAdd(sums + 2 * u + 1, b);
+    }
+}
+
 // ---- element-wise magnitude / unit phase of a complex spectrogram ----------------------------
 __global__ void mag_phase_kernel(const float2* __restrict__ x, long long n, float* __restrict__ mag, float2* __restrict__ ph) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -579,6 +616,28 @@ int rced_mag_phase(int device, const float* X, int64_t n, float* mag, float* pha
     count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_mag_phase launch");
+}
+
+int rced_sdr_sums(int device, const float* ref, const int64_t* ref_off, const float* est, const int64_t* est_off,
+                  const int32_t* len, int n_utt, int64_t max_len, double* sums, void* stream) {
+    if (n_utt < 0 || max_len < 0) return fail(RCED_ERR_ARG, "negative size");
+    if (n_utt == 0) return RCED_OK;
+    if (!ref || !ref_off || !est || !est_off || !len || !sums) return fail(RCED_ERR_ARG, "null pointer");
+    if (n_utt > 65535) return fail(RCED_ERR_ARG, "at most 65535 utterances per call");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(RCED_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    DeviceGuard guard(device);
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)n_utt * 2 * sizeof(double), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(sdr sums)");
+    long long chunks = (max_len + 256 * 16 - 1) / (256 * 16);   // ~16 samples per thread
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    sdr_sums_kernel<<<dim3((unsigned)chunks, (unsigned)n_utt), 256, 0, (cudaStream_t)stream>>>(
+        ref, est, reinterpret_cast<const long long*>(ref_off), reinterpret_cast<const long long*>(est_off), len, sums);
+    count_launch();
+    e = cudaGetLastError();
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_sdr_sums launch");
 }
 
 int rced_ffma_peak(int device, int iters, double* tflops) {

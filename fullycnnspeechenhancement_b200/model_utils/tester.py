@@ -11,7 +11,7 @@ from .. import audio_io
 from ..config import section_with
 from . import fold
 from .model import build_model
-from .utils import SDR, AudioReBuild, AverageMeter
+from .utils import SDR, AudioReBuild, AverageMeter, sdr_batch
 
 
 class BaseTester(object):
@@ -86,9 +86,11 @@ class FullyCNNTester(BaseTester):
             audio_bins = valid_loader.bins[index]
             denoise = eng.enhance(mix_sig)
             denoise = [np.asarray(d[:len(c)], dtype=np.float64) for d, c in zip(denoise, clean_sig)]
+            lens = [min(len(c), len(d)) for c, d in zip(clean_sig, denoise)]
+            scores = sdr_batch([np.asarray(c[:n]) for c, n in zip(clean_sig, lens)], [d[:n] for d, n in zip(denoise, lens)],
+                               device=eng.device.index)
             for i in range(len(audio_bins)):
-                n = min(len(clean_sig[i]), len(denoise[i]))
-                self.sdr_score.update(sdr(np.asarray(clean_sig[i][:n]), denoise[i][:n]))
+                self.sdr_score.update(float(scores[i]))
                 name = os.path.basename(valid_loader.dataset.item_name(audio_bins[i]))
                 audio_io.write_wav(os.path.join(self.audio_save_path, name), clean_sig[i], self.sample_rate)
                 audio_io.write_wav(os.path.join(self.audio_save_path, name.replace(".wav", "_mix.wav")), mix_sig[i], self.sample_rate)

@@ -182,6 +182,15 @@ int rced_enhance(rced_handle* h, const float* wav, const int64_t* wav_off, const
  *   X DEVICE float32[n][2]; mag DEVICE float32[n] or NULL; phase DEVICE float32[n][2] or NULL */
 int rced_mag_phase(int device, const float* X, int64_t n, float* mag, float* phase, void* stream);
 
+/* Energy sums of the SDR score of n_utt (reference, estimate) pairs: sums[u] = { sum ref^2,
+ * sum (est - ref)^2 } over len[u] samples, accumulated in float64.  The score of
+ * SDR.sdr (model_utils/utils.py:68-78; used at model_utils/tester.py:136-139) is
+ * 10*log10(sums[u][0] / (sums[u][1] + FLT_EPSILON)).
+ *   ref, est  DEVICE float32, concatenated signals;  ref_off, est_off  DEVICE int64[n_utt]
+ *   len       DEVICE int32[n_utt];  max_len = max(len) (grid sizing);  sums DEVICE float64[n_utt][2] */
+int rced_sdr_sums(int device, const float* ref, const int64_t* ref_off, const float* est, const int64_t* est_off,
+                  const int32_t* len, int n_utt, int64_t max_len, double* sums, void* stream);
+
 /* ---- measurement helpers --------------------------------------------------------- */
 
 /* Dense FP32 FFMA microbenchmark (independent register chains, one CTA set per SM).

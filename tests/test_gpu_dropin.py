@@ -168,3 +168,17 @@ def test_model_objects_and_frozen_graph(workdir, tmp_path):
         FullyCNNSEModelV3(is_training=False)(x)                      # no weights loaded
     with pytest.raises(KeyError):
         FullyCNNSEModelV3(is_training=False).set_weights({"decode_final/kernel": x})
+
+
+def test_sdr_batch_matches_the_reference_formula():
+    """rced_sdr_sums (float64 sums on the GPU) against SDR.sdr (model_utils/utils.py:68-78 of the reference)."""
+    from fullycnnspeechenhancement_b200.model_utils.utils import SDR, sdr_batch
+    rng = np.random.default_rng(3)
+    refs = [rng.normal(0, 0.3, n).astype(np.float32) for n in (1, 255, 4096, 32000, 100001)]
+    ests = [r + rng.normal(0, s, len(r)).astype(np.float32) for r, s in zip(refs, (0.1, 0.01, 0.3, 1e-3, 0.05))]
+    ests[1] = refs[1].copy()                                     # perfect estimate: finite thanks to the epsilon
+    got = sdr_batch(refs, ests)
+    want = np.array([SDR()(r.astype(np.float64), e.astype(np.float64)) for r, e in zip(refs, ests)])
+    assert got.shape == (5,) and np.all(np.isfinite(got))
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    assert sdr_batch([], []).shape == (0,)
