@@ -179,7 +179,18 @@ class Enhancer(object):
         wav_off = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64)
         if chunk_utts is None:
             chunk_utts = n
-        bounds = list(range(0, n, chunk_utts)) + [n]
+        if np.ndim(chunk_utts) == 0:
+            bounds = list(range(0, n, int(chunk_utts))) + [n]
+        else:
+            # explicit chunk sizes (the last one is repeated as often as needed): small first and last chunks
+            # shorten the part of the host pipeline that cannot overlap (first upload, last download)
+            sizes = [int(c) for c in chunk_utts]
+            if not sizes or min(sizes) < 1:
+                raise ValueError("chunk sizes must be positive")
+            bounds, i = [0], 0
+            while bounds[-1] < n:
+                bounds.append(min(n, bounds[-1] + sizes[min(i, len(sizes) - 1)]))
+                i += 1
         row_tables, spans, pos = [], [], 0
         for c0, c1 in zip(bounds[:-1], bounds[1:]):
             ro = np.concatenate([[0], np.cumsum(frames[c0:c1])]).astype(np.int64)
