@@ -233,6 +233,27 @@ def test_stream_chunked_equals_whole(dev, engines):
     assert rebuild.sdr_db(whole, chunked) >= 100.0
 
 
+def test_online_streaming_equals_whole(dev, engines):
+    """Block-by-block enhancement (StreamingEnhancer: arbitrary push sizes, 13-hop look-back, 6-hop
+    look-ahead) returns the whole-file result to float32 rounding, sample for sample."""
+    from fullycnnspeechenhancement_b200.streaming import StreamingEnhancer
+    eng = engines["FullyCNNV3"][0]
+    L = 8000 * 20 + 77
+    wv = noisy_utterance(56, L)
+    whole = eng.enhance([wv])[0]
+    st = StreamingEnhancer(eng, block=4096)
+    rng = np.random.default_rng(1)
+    outs, pos = [], 0
+    while pos < L:
+        n = int(rng.integers(100, 9000))
+        outs.append(st.push(wv[pos:pos + n]))
+        pos += n
+    outs.append(st.flush())
+    got = np.concatenate(outs)
+    assert len(got) == L
+    assert rebuild.sdr_db(whole, got) >= 100.0
+
+
 def test_golden_fixtures_on_gpu(dev, engines, golden_dir):
     """Committed vectors: reference-generated STFT/rebuild, oracle-generated network outputs."""
     import os

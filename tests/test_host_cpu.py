@@ -311,3 +311,41 @@ def test_dataset_sampler_loader_follow_the_reference(tmp_path):
     am.update(4.0, n=3)
     assert am.sum == 6.0 and am.count == 4 and am.avg == 1.5
     assert AudioParser(8000, 32, 16).window_s == 0.032
+
+
+def test_streaming_bookkeeping_with_a_stand_in_engine():
+    """StreamingEnhancer cuts halo'd pieces on the hop grid, returns every sample exactly once and in
+    order, and keeps no more history than the look-back (checked with an engine that marks each
+    sample with its absolute position, no GPU needed)."""
+    from fullycnnspeechenhancement_b200.streaming import LOOK_AHEAD, LOOK_BACK, StreamingEnhancer
+
+    class Echo(object):
+        def __init__(self):
+            self.calls = []
+
+        def enhance(self, waves):
+            self.calls.append(len(waves[0]))
+            return [np.asarray(w, np.float32) * 2.0 for w in waves]
+
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=50000).astype(np.float32)
+    eng = Echo()
+    st = StreamingEnhancer(eng, block=1000)            # rounded down to 896 = 7 hops
+    assert st.block == 896 and st.latency_samples == 896 + LOOK_AHEAD
+    got, pos, pushed = [], 0, 0
+    while pos < len(x):
+        n = int(rng.integers(1, 3000))
+        out = st.push(x[pos:pos + n])
+        pos += n
+        pushed = min(pos, len(x))
+        got.append(out)
+        done = sum(len(g) for g in got)
+        assert done % 896 == 0 and done <= max(0, pushed - LOOK_AHEAD)        # only final samples are returned ...
+        assert pushed - done < 896 + LOOK_AHEAD + 3000                        # ... and without undue delay
+        assert len(st._buf) <= LOOK_BACK + 896 + LOOK_AHEAD + 3000            # bounded history
+    got.append(st.flush())
+    y = np.concatenate(got)
+    assert len(y) == len(x) and np.array_equal(y, 2.0 * x)
+    assert max(eng.calls) <= LOOK_BACK + 16 * 128 + LOOK_AHEAD
+    with pytest.raises(ValueError):
+        StreamingEnhancer(eng, block=64)
