@@ -268,6 +268,9 @@ def main():
     ap.add_argument("--skip-in-global", action="store_true", help="park skips in global scratch instead of TMEM")
     ap.add_argument("--variant", default=DEFAULT_VARIANT, choices=["ffma", "tc"],
                     help="network kernel: FP32 FFMA, or tcgen05 tensor cores with the FP16 x3 split")
+    ap.add_argument("--sweep-utterances", type=int, default=0,
+                    help="also time one job of this many 4 s utterances partitioned over the ranks (BASELINE.json configs[4]: "
+                         "100000), device-resident, and report it under 'sweep'")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -429,6 +432,28 @@ def main():
                              rows, tc_status),
         "clocks": clocks,
     }
+    if args.sweep_utterances > 0:
+        # BASELINE.json configs[4]: a fixed job partitioned across the ranks (strong scaling).  The job is cut into
+        # batches of N_UTT utterances (the device-resident pool tiled; H2D is not in the timed region), batch i goes to
+        # rank i % world, no collective.
+        n_batches = (args.sweep_utterances + N_UTT - 1) // N_UTT
+        mine = len(range(rank, n_batches, world))
+        step_device()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(mine):
+            step_device()
+        s1.record()
+        barrier()
+        job_ms = max_over_ranks(s0.elapsed_time(s1))
+        job_utts = n_batches * N_UTT
+        result["sweep"] = {"workload": "R-CED V2, one job of %d synthetic 4 s utterances (%d batches of %d) partitioned over %d "
+                                       "B200 (BASELINE.json configs[4]); inputs resident in HBM (pool tiled)" %
+                                       (job_utts, n_batches, N_UTT, world),
+                           "utterances": job_utts, "audio_seconds": job_utts * UTT_SAMPLES / SAMPLE_RATE,
+                           "job_seconds": job_ms * 1e-3, "scaling": "strong",
+                           "value": job_utts * UTT_SAMPLES / SAMPLE_RATE / (job_ms * 1e-3), "unit": UNIT}
     if not args.no_cpu_baseline and world == 1:
         from oracle import network as onet
         result["cpu_baseline"] = cpu_baseline(pool, onet.random_weights(NET_WORK, seed=0, randomize_bn=False))
