@@ -14,12 +14,16 @@
 //  * FP32 accuracy from FP16 tensor cores by an error-compensated split: activations and
 //    weights are stored as hi + lo FP16 pairs and every K step issues A_hi x [Whi | Wlo]
 //    (N = 2 NP) and A_lo x Whi (N = NP) into FP32 accumulators in tensor memory;
-//  * warp roles: warp 0 issues the MMAs (one elected lane), warp 1 streams the next layer's
-//    weight tiles from L2 with bulk async copies into a double buffer, warps 4-11 are two
-//    epilogue groups (tcgen05.ld -> bias, skip, ReLU -> hi/lo split -> st.shared of the next
-//    layer's planes).  Layers overlap tile by tile: the epilogue of (layer, tile t) starts when
-//    the MMAs of tile t+1 have completed (they read tile t's halo rows, planes are updated in
-//    place) and the MMAs of (layer+1, t) start when the epilogues of tiles t-1..t+1 are done;
+//  * warp roles (rced_tc.cuh): warps 0, 3, 5 issue the MMAs (one elected lane each, row tiles of the
+//    global (step, tile) sequence round robin, all descriptor arithmetic in the uniform datapath from
+//    constant-memory tables), warp 1 streams the next layers' weight tiles from L2 with bulk async
+//    copies into a double buffer, warp 2 is the dependency scout (waits on the mbarriers of every
+//    (step, tile) in issue order and publishes a counter), warp 4 prefetches the next batch's input
+//    rows, warps 6-21 are four epilogue groups (tcgen05.ld -> bias, skip, ReLU -> hi/lo split ->
+//    st.shared of the next layer's planes).  Layers overlap tile by tile: the epilogue of (layer,
+//    tile t) starts when the MMAs of tiles t-1, t, t+1 have completed (they read tile t's rows, the
+//    neighbours as halo; planes are updated in place) and the MMAs of (layer+1, t) start when the
+//    epilogues of tiles t-1..t+1 are done;
 //  * the (1,129) output layer runs "taps in N with row-shifted accumulation" (rced_tc.cuh): five MMAs
 //    per row tile whose A descriptors are shifted by -64 .. +64 rows accumulate E[r][n] =
 //    sum_i X[r + 32 (i - 2)] . W[32 i + n] into 32 columns, and the epilogue forms out[b] =
@@ -588,8 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         // check, descriptor set-up, commit) or between two steps (the step prologue) would leave the
         // pipe idle; with three threads and 8 tiles per step the step boundaries of the threads fall
         // at different times, and one thread prepares while the others issue.
-        // Per step the start-address words of every unit's A and B descriptors are built once into
-        // registers (fully unrolled, kMaxUnits slots): issuing a unit is an add and the MMA pair.
+        // A unit is a constant-memory load, three uniform adds and the MMA pair (see IssueTab).
         const int iss = warp == 0 ? 0 : (warp == 3 ? 1 : warp - 3);
         if (elect_one()) {
             const uint32_t flag = bars + 8 * kFlagSlot;

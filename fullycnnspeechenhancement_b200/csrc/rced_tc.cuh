@@ -99,8 +99,8 @@ RCED_HD constexpr int max_units(int arch) {
         if (step_units(arch, i) > m) m = step_units(arch, i);
     return m;
 }
-constexpr int kMaxUnits = 18;   // register slots of the MMA issue loop
-constexpr int kTabStride = 20;  // words per step in the A-descriptor table (kMaxUnits rounded up to 16 bytes)
+constexpr int kMaxUnits = 18;   // most units of a step
+constexpr int kTabStride = 20;  // words per step in the constant-memory A-descriptor table
 static_assert(n_steps(1) % 2 == 0 && n_steps(2) % 2 == 0 && n_steps(3) % 2 == 0, "step s must always use weight buffer s & 1");
 static_assert(max_units(1) <= kMaxUnits && max_units(2) <= kMaxUnits && max_units(3) <= kMaxUnits, "raise kMaxUnits");
 
@@ -144,9 +144,7 @@ RCED_HD constexpr size_t skip_floats_per_cta(int arch) { return (size_t)skip_c8_
 RCED_HD constexpr int pad128(int x) { return (x + 127) & ~127; }
 constexpr int smem_act_off = kFrontPad;   // activation planes, behind the zero rows
 RCED_HD constexpr int smem_w_off(int arch, int buf) { return kFrontPad + kActBytes + buf * pad128(max_step_w_bytes(arch)); }
-RCED_HD constexpr int smem_tab_off(int arch) { return smem_w_off(arch, 2); }                        // uint32[n_steps][kTabStride]
-RCED_HD constexpr int smem_step_off(int arch) { return smem_tab_off(arch) + pad128(4 * kTabStride * n_steps(arch)); }   // int4[n_steps]
-RCED_HD constexpr int smem_bias_off(int arch) { return smem_step_off(arch) + pad128(16 * n_steps(arch)); }     // float[n_steps][32]
+RCED_HD constexpr int smem_bias_off(int arch) { return smem_w_off(arch, 2); }                                   // float[n_steps][32]
 RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 128 * n_steps(arch); }             // float[2][kRows]: the two partial sums of every output row
 RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + 2 * kRows * 4; }                    // long long[2][kFB][2]
 RCED_HD constexpr int smem_bar_off(int arch) { return smem_bnd_off(arch) + 256; }                              // mbarriers
