@@ -389,6 +389,29 @@ def main():
     e2e_value = world * audio_s_per_step * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
+    sweep = None
+    if args.sweep_utterances > 0:   # every rank takes part (before the non-zero ranks leave)
+        # BASELINE.json configs[4]: a fixed job partitioned across the ranks (strong scaling).  The job is cut into
+        # batches of N_UTT utterances (the device-resident pool tiled; H2D is not in the timed region), batch i goes to
+        # rank i % world, no collective.
+        n_batches = (args.sweep_utterances + N_UTT - 1) // N_UTT
+        mine = len(range(rank, n_batches, world))
+        step_device()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(mine):
+            step_device()
+        s1.record()
+        barrier()
+        job_ms = max_over_ranks(s0.elapsed_time(s1))
+        job_utts = n_batches * N_UTT
+        sweep = {"workload": "R-CED V2, one job of %d synthetic 4 s utterances (%d batches of %d) partitioned over %d "
+                                       "B200 (BASELINE.json configs[4]); inputs resident in HBM (pool tiled)" %
+                                       (job_utts, n_batches, N_UTT, world),
+                           "utterances": job_utts, "audio_seconds": job_utts * UTT_SAMPLES / SAMPLE_RATE,
+                           "job_seconds": job_ms * 1e-3, "scaling": "strong",
+                           "value": job_utts * UTT_SAMPLES / SAMPLE_RATE / (job_ms * 1e-3), "unit": UNIT}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -432,28 +455,8 @@ def main():
                              rows, tc_status),
         "clocks": clocks,
     }
-    if args.sweep_utterances > 0:
-        # BASELINE.json configs[4]: a fixed job partitioned across the ranks (strong scaling).  The job is cut into
-        # batches of N_UTT utterances (the device-resident pool tiled; H2D is not in the timed region), batch i goes to
-        # rank i % world, no collective.
-        n_batches = (args.sweep_utterances + N_UTT - 1) // N_UTT
-        mine = len(range(rank, n_batches, world))
-        step_device()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(mine):
-            step_device()
-        s1.record()
-        barrier()
-        job_ms = max_over_ranks(s0.elapsed_time(s1))
-        job_utts = n_batches * N_UTT
-        result["sweep"] = {"workload": "R-CED V2, one job of %d synthetic 4 s utterances (%d batches of %d) partitioned over %d "
-                                       "B200 (BASELINE.json configs[4]); inputs resident in HBM (pool tiled)" %
-                                       (job_utts, n_batches, N_UTT, world),
-                           "utterances": job_utts, "audio_seconds": job_utts * UTT_SAMPLES / SAMPLE_RATE,
-                           "job_seconds": job_ms * 1e-3, "scaling": "strong",
-                           "value": job_utts * UTT_SAMPLES / SAMPLE_RATE / (job_ms * 1e-3), "unit": UNIT}
+    if sweep is not None:
+        result["sweep"] = sweep
     if not args.no_cpu_baseline and world == 1:
         from oracle import network as onet
         result["cpu_baseline"] = cpu_baseline(pool, onet.random_weights(NET_WORK, seed=0, randomize_bn=False))
