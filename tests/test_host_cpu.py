@@ -349,3 +349,15 @@ def test_streaming_bookkeeping_with_a_stand_in_engine():
     assert max(eng.calls) <= LOOK_BACK + 16 * 128 + LOOK_AHEAD
     with pytest.raises(ValueError):
         StreamingEnhancer(eng, block=64)
+
+
+def test_bench_has_no_collective_after_the_non_zero_ranks_leave():
+    """bench.py lets ranks != 0 return once the timed sections are over; a barrier or all-reduce behind
+    that point hangs every multi-GPU run (it happened once).  Checked on the source."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    main = src[src.index("def main():"):]
+    leave = main.index("    if rank != 0:\n        if world > 1:\n            dist.destroy_process_group()\n        return")
+    tail = main[leave + 10:]
+    tail = tail[tail.index("return") + 6:]
+    for call in ("barrier()", "max_over_ranks(", "dist.all_reduce", "dist.barrier", "dist.broadcast"):
+        assert call not in tail, call
