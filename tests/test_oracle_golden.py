@@ -126,3 +126,73 @@ def test_network_padding_invariance():
     both = network.forward(arch, w, batch)
     # frames whose 8-tap time window stays inside the 6 valid frames (+ zero padding == SAME padding)
     assert np.allclose(alone[0, :2], both[0, :2], atol=1e-12)
+
+
+@pytest.mark.parametrize("arch", ["FullyCNN", "FullyCNNV2", "FullyCNNV3"])
+def test_network_third_evaluator_scipy(arch):
+    """A third, independently written evaluation of the graph: per (cin, cout) pair
+    ``scipy.signal.correlate2d`` in 'full' mode, cropped to TensorFlow's SAME window (output pixel i reads
+    inputs i - (k-1)//2 ... i + k-1 - (k-1)//2), layer wiring re-read from model_utils/model.py rather
+    than taken from the oracle's executor.  TensorFlow itself is absent (parity unpinned, DESIGN.md 3);
+    this pins the oracle's conv / padding / BN / skip arithmetic against another formulation."""
+    from scipy.signal import correlate2d
+    w = network.random_weights(arch, seed=21, randomize_bn=True)
+    rng = np.random.default_rng(4)
+    T = 6
+    x = np.abs(rng.normal(0, 2, (T, 129))).astype(np.float64)
+
+    def conv_same(inp, kernel, bias):                       # inp [cin][T][F], kernel HWIO
+        kh, kw, cin, cout = kernel.shape
+        out = np.zeros((cout, T, 129))
+        for o in range(cout):
+            for c in range(cin):
+                full = correlate2d(inp[c], kernel[:, :, c, o].astype(np.float64), mode="full")
+                # full[i + kh - 1 - pt] is the response centred so that SAME's "pt before" holds
+                r0, c0 = kh - 1 - (kh - 1) // 2, kw - 1 - (kw - 1) // 2
+                out[o] += full[r0:r0 + T, c0:c0 + 129]
+            out[o] += np.float64(bias[o])
+        return out
+
+    def bn(y, s):
+        g_, b_, m_, v_ = (w[s + "/batch_norm/" + n].astype(np.float64) for n in ("gamma", "beta", "moving_mean", "moving_variance"))
+        return (y - m_[:, None, None]) / np.sqrt(v_[:, None, None] + 1e-3) * g_[:, None, None] + b_[:, None, None]
+
+    def cbr(inp, s, norm=True, act=True, skip=None):
+        y = conv_same(inp, w[s + "/kernel"], w[s + "/bias"])
+        if norm:
+            y = bn(y, s)
+        if skip is not None:
+            y = y + skip
+        return np.maximum(y, 0) if act else y
+
+    a = x[None]
+    if arch == "FullyCNNV3":                                 # model.py:64-96
+        def block(inp, name, skip=None):
+            e = cbr(cbr(cbr(inp, name + "_encode_1"), name + "_encode_2"), name + "_decode")
+            return e if skip is None else e + skip
+        c1 = block(a, "CE1")
+        c2 = block(c1, "CE2")
+        c3 = block(c2, "CE3")
+        d = block(block(c3, "CD1", c2), "CD2", c1)
+        out = cbr(d, "decode_final", norm=False, act=False)
+    elif arch == "FullyCNNV2":                               # model.py:32-61
+        e = [a]
+        for i in range(1, 9):
+            e.append(cbr(e[-1], "encode_%d" % i))
+        d = e[8]
+        for i in range(1, 8):
+            d = cbr(d, "decode_%d" % i, skip=e[8 - i])
+        out = cbr(d, "decode_8", norm=False, act=False)
+    else:                                                    # model.py:6-29 (the fifth encoder scope is "encode_8")
+        e1 = cbr(a, "encode_1")
+        e2 = cbr(e1, "encode_2")
+        e3 = cbr(e2, "encode_3")
+        e4 = cbr(e3, "encode_4")
+        e5 = cbr(e4, "encode_8")
+        d = cbr(e5, "decode_1", skip=e4)
+        d = cbr(d, "decode_2", skip=e3)
+        d = cbr(d, "decode_3", skip=e2)
+        d = cbr(d, "decode_4", skip=e1)
+        out = cbr(d, "decode_5", norm=False, act=False)
+    ref = network.forward(arch, w, x[None, :, :, None], np.float64)[0, :, :, 0]
+    assert np.abs(out[0] - ref).max() <= 1e-10 * np.abs(ref).max()
