@@ -35,17 +35,21 @@ class AudioParser(object):
         uniform(0, 2) draw), a longer one is cropped at a random start; then it is scaled so that
         sum(speech^2) / sum(noise^2) == 10^(snr/10).  Draws come from numpy's global generator in
         the reference's order, so a seeded run mixes identically."""
-        if len(speech) >= len(noise):
-            rounds = int(np.ceil((len(speech) - len(noise)) / len(noise)))
-            for _ in range(rounds):
-                noise = np.concatenate((noise, noise * np.random.uniform(0, 2)))
-            noise = noise[:len(speech)]
+        n_speech, n_noise = len(speech), len(noise)
+        if n_speech < n_noise:
+            first = np.random.randint(0, n_noise - n_speech)
+            bed = noise[first:first + n_speech]
         else:
-            start = np.random.randint(0, len(noise) - len(speech))
-            noise = noise[start:start + len(speech)]
-        p_sig = np.sum(abs(speech) ** 2)
-        p_back = np.sum(abs(noise) ** 2)
-        return speech + np.sqrt(p_sig / (10 ** (self.snr / 10)) / p_back) * noise
+            bed = noise
+            doublings = int(np.ceil((n_speech - n_noise) / n_noise))   # of the ORIGINAL length, as in the reference
+            for _ in range(doublings):
+                gain = np.random.uniform(0, 2)
+                bed = np.concatenate((bed, bed * gain))
+            bed = bed[:n_speech]
+        speech_energy = np.sum(abs(speech) ** 2)
+        noise_energy = np.sum(abs(bed) ** 2)
+        target_noise_energy = speech_energy / (10 ** (self.snr / 10))
+        return speech + np.sqrt(target_noise_energy / noise_energy) * bed
 
     def parse_audio(self, sig):
         return self.extractor.compute_spectrogram(sig, self.sample_rate, window_s=self.window_s,
@@ -124,41 +128,42 @@ class Sampler(object):
     """Batch index bins in random order (data_loader.py:128-160).  ``drop_last`` cuts the ragged
     tail off the dataset's item list; otherwise the list is EXTENDED with its last items up to the
     next multiple of the batch size -- a whole extra batch when it already divides, as in the
-    reference (int(n / b) + 1 batches)."""
+    reference (int(n / b) + 1 batches).  The dataset's ``item_list`` is modified in place, which is
+    what makes ``len(dataset)`` a multiple of the batch size afterwards."""
 
     def __init__(self, dataset, batch_size, start_index=0, drop_last=False):
-        self.dataset = dataset
-        self.batch_size = batch_size
-        self.start_index = start_index
-        n = len(self.dataset)
+        self.dataset, self.batch_size, self.start_index = dataset, batch_size, start_index
+        items = self.dataset.item_list
+        count = len(items)
         if drop_last:
-            last_size = n % batch_size
-            # [:-0] would empty the list: the reference does exactly that when n divides evenly
-            self.dataset.item_list = self.dataset.item_list[:-last_size]
+            tail = count % batch_size
+            # a zero tail gives items[:-0] == []: the reference empties the list in that case, so do we
+            self.dataset.item_list = items[:-tail]
         else:
-            last_size = (int(n / batch_size) + 1) * batch_size - n
-            self.dataset.item_list.extend(self.dataset.item_list[-last_size:])
-        ids = list(range(len(self.dataset)))
-        self.bins = [ids[i:i + self.batch_size] for i in range(0, len(ids), self.batch_size)]
-        self.indices = (np.random.permutation(len(self.bins) - self.start_index) + self.start_index).tolist()
+            missing = (count // batch_size + 1) * batch_size - count
+            items.extend(items[-missing:])
+        total = len(self.dataset)
+        self.bins = [list(range(lo, min(lo + batch_size, total))) for lo in range(0, total, batch_size)]
+        order = np.random.permutation(len(self.bins) - start_index) + start_index
+        self.indices = order.tolist()
 
     def __iter__(self):
-        for x in self.indices:
-            batch_ids = self.bins[x]
-            np.random.shuffle(batch_ids)
-            yield batch_ids
+        for which in self.indices:
+            members = self.bins[which]
+            np.random.shuffle(members)       # in place, like the reference: the bin stays shuffled
+            yield members
 
     def __len__(self):
         return len(self.bins) - self.start_index
+
+    def iter_num(self):
+        return len(self.indices)
 
     def reset_start_index(self, start_index):
         self.start_index = start_index
 
     def __call__(self, *args, **kwargs):
         return self
-
-    def iter_num(self):
-        return len(self.indices)
 
 
 class DataLoader(object):
@@ -205,18 +210,19 @@ class DataLoader(object):
         assert mix.shape == clean.shape
         return mix, clean, mix_sig, clean_sig
 
+    def _index_groups(self):
+        if self.sampler is None:
+            return self.bins
+        if self.sampler.batch_size != self.batch_size:
+            self.batch_size = self.sampler.batch_size
+            print("Warrning: sampler.batch_size != batch_size. batch_size changed!")
+        return self.sampler
+
     def __iter__(self):
-        if self.sampler is not None:
-            if self.sampler.batch_size != self.batch_size:
-                self.batch_size = self.sampler.batch_size
-                print("Warrning: sampler.batch_size != batch_size. batch_size changed!")
-            groups = self.sampler
-        else:
-            groups = self.bins
-        for index_list in groups:
-            self.pool_process(index_list)
-            results, self.q = self.q, []
-            yield self.collect_fn(results)
+        for group in self._index_groups():
+            self.pool_process(group)
+            fetched, self.q = self.q, []
+            yield self.collect_fn(fetched)
 
     def __len__(self):
         return len(self.sampler) if self.sampler is not None else len(self.bins)

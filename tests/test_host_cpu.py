@@ -361,3 +361,31 @@ def test_bench_has_no_collective_after_the_non_zero_ranks_leave():
     tail = tail[tail.index("return") + 6:]
     for call in ("barrier()", "max_over_ranks(", "dist.all_reduce", "dist.barrier", "dist.broadcast"):
         assert call not in tail, call
+
+
+def test_entry_point_helpers_on_the_cpu(tmp_path):
+    """test.py's loader construction from a cfg and infer.py's reference feed layout (the reshape quirk),
+    without a GPU."""
+    import types
+    from fullycnnspeechenhancement_b200.config import load_conf_info
+    from fullycnnspeechenhancement_b200.infer import _as_reference_feeds
+    from fullycnnspeechenhancement_b200.test import build_loader
+    manifest = str(tmp_path / "m.testset")
+    _write_manifest(manifest, [{"clean_audio_filepath": "c%d.wav" % i, "mix_audio_filepath": "m%d.wav" % i, "duration": 1.0 + i}
+                               for i in range(5)])
+    cfg = tmp_path / "t.cfg"
+    cfg.write_text("[testing]\nbatch_size=2\ncheckpoint_filepath=x\n[model]\nnet_arch=RCED\nnet_work=FullyCNNV2\n"
+                   "[data]\ntest_manifest_path=%s\nsnr=5\nsample_rate=8000\nfeature_dim=129\nwindow_ms=32\nstride_ms=16\n"
+                   "audio_save_path=%s\n" % (manifest, tmp_path / "out"))
+    loader = build_loader(load_conf_info(str(cfg)), num_works=3)
+    ds = loader.dataset
+    assert len(ds) == 5 and ds.noise_manifest is None and ds.snr == 5.0 and ds.sample_rate == 8000 and ds.complex
+    assert (ds.window_s, ds.stride_s) == (0.032, 0.016) and loader.bins == [[0, 1], [2, 3], [4]] and loader.num_works == 3
+    # infer.py:57-61: [F,T] arrays reshaped (not transposed) to (1,T,F,1) / (1,T,F)
+    rng = np.random.default_rng(0)
+    spec = rng.normal(size=(129, 7)) + 1j * rng.normal(size=(129, 7))
+    ext = types.SimpleNamespace(power_spectrum=stft.power_spectrum, divide_phase=stft.divide_phase)
+    mag, ph = _as_reference_feeds(spec, ext)
+    assert mag.shape == (1, 7, 129, 1) and ph.shape == (1, 7, 129)
+    assert np.array_equal(mag.reshape(-1), np.abs(spec).reshape(-1))            # memory order kept: a reshape, no transpose
+    assert np.allclose(ph.reshape(129, 7) * np.abs(spec), spec)
