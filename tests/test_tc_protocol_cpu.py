@@ -1,0 +1,186 @@
+"""CPU: race check of the tensor-core kernel's synchronisation protocol on a happens-before model.
+
+The kernel (csrc/rced_net_tc.cu) updates its activation planes in place while MMAs of neighbouring row
+tiles, of the next layer and of the next batch are in flight; what keeps that safe is a handful of waits
+(the three commits an epilogue awaits, the scout's cumulative act_ready waits, final_done before the next
+batch is staged, in_ready before its first layer).  This test rebuilds those waits as a graph over the
+events of two consecutive batches -- M(b,s,t): the MMAs of (step, row tile); E(b,s,t): its epilogue;
+S(b,g): epilogue group g staging batch b's input -- takes the rows and planes every event reads and
+writes from the library's own layout tables (rced_tc_layout), and asserts that every pair of conflicting
+accesses (plane write vs plane read or write on overlapping rows; accumulator write vs read) is ordered
+by the transitive closure.  It would have caught the race of the two-commit wait with three issuing
+threads (tile t-1's MMAs not awaited), which the GPU tests passed."""
+import itertools
+
+import pytest
+
+from fullycnnspeechenhancement_b200 import _lib
+from fullycnnspeechenhancement_b200.model_utils import fold
+from oracle import network
+
+TILES, GROUPS = 8, 4
+
+
+def _layout(arch):
+    import tc_emulator
+    return tc_emulator.layout(_lib.lib(), arch)
+
+
+def _accesses(name):
+    """Per step: rows/planes read by the MMAs of a tile (relative to the tile's first row), planes written
+    by its epilogue."""
+    lay = _layout(fold.arch_id(name))
+    table = network.layer_table(name)
+    P16, ns = lay["plane16"], lay["ns"]
+    steps = []
+    for s, st in enumerate(lay["steps"]):
+        reads = set()                                         # (plane, row shift)
+        for u in range(st["units"]):
+            off, lbo = lay["units"][st["unit_base"] + u]
+            for o in (off, off + lbo):
+                plane = (o + P16 // 2) // P16
+                reads.add((plane, o - plane * P16))
+        if st["final"]:                                       # odd-frame copy: two planes further
+            reads |= {(p + 2, sh) for p, sh in set(reads)}
+            writes = set()
+        else:
+            cg = (table[s]["cout"] + 7) // 8
+            writes = set(range(cg))
+            if s == ns - 2:                                   # last conv layer: even and odd copies
+                writes |= {p + 2 for p in range(cg)}
+        steps.append(dict(reads=reads, writes=writes, final=st["final"]))
+    return steps
+
+
+def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_waits_final_done=True):
+    ns = len(steps)
+    nodes, edges = [], {}
+
+    def node(*k):
+        if k not in edges:
+            edges[k] = set()
+            nodes.append(k)
+        return k
+
+    def before(u, v):
+        edges[node(*u)].add(node(*v))
+
+    for b in range(2):
+        for g in range(GROUPS):
+            node("S", b, g)
+        for s in range(ns):
+            for t in range(TILES):
+                node("M", b, s, t)
+                node("E", b, s, t)
+    for b in range(2):
+        for s in range(ns):
+            for t in range(TILES):
+                # epilogue waits (mbar_wait3 / the output layer's single wait)
+                need = [t] if steps[s]["final"] else [t, t + 1] + ([t - 1] if wait_prev_tile else [])
+                for tt in need:
+                    if 0 <= tt < TILES:
+                        before(("M", b, s, tt), ("E", b, s, t))
+                # scout: cumulative act_ready waits of the step before (of the batch before for step 0)
+                prev = (b, s - 1) if s > 0 else ((b - 1, ns - 1) if b > 0 and scout_waits_final_epilogue else None)
+                if prev is not None:
+                    for tt in range(0, min(t + 1, TILES - 1) + 1):
+                        before(("E", prev[0], prev[1], tt), ("M", b, s, t))
+                if s == 0:                                    # in_ready: every group has staged
+                    for g in range(GROUPS):
+                        before(("S", b, g), ("M", b, 0, t))
+        # program order of an epilogue group: tiles g, g + 4 of every step; staging between the two
+        # output-layer tiles
+        for g in range(GROUPS):
+            seq = [("S", 0, g)] if b == 0 else []
+            for s in range(ns):
+                seq.append(("E", b, s, g))
+                if s == ns - 1 and b == 0:
+                    seq.append(("S", 1, g))
+                seq.append(("E", b, s, g + GROUPS))
+            if b == 1:
+                seq = [("E", 0, ns - 1, g + GROUPS)] + seq
+            for u, v in zip(seq[:-1], seq[1:]):
+                before(u, v)
+    if stage_waits_final_done:                                # final_done: every MMA of the output layer
+        for g in range(GROUPS):
+            for t in range(TILES):
+                before(("M", 0, ns - 1, t), ("S", 1, g))
+    return nodes, edges
+
+
+def _closure(nodes, edges):
+    index = {n: i for i, n in enumerate(nodes)}
+    reach = [0] * len(nodes)
+    order, seen = [], set()
+    for root in nodes:                                        # iterative post-order
+        if root in seen:
+            continue
+        stack = [(root, iter(edges[root]))]
+        seen.add(root)
+        while stack:
+            n, it = stack[-1]
+            nxt = next(it, None)
+            if nxt is None:
+                order.append(n)
+                stack.pop()
+            elif nxt not in seen:
+                seen.add(nxt)
+                stack.append((nxt, iter(edges[nxt])))
+    for n in order:                                           # successors first
+        m = 0
+        for v in edges[n]:
+            m |= reach[index[v]] | (1 << index[v])
+        reach[index[n]] = m
+    return lambda u, v: bool(reach[index[u]] >> index[v] & 1)
+
+
+def _races(steps, **variant):
+    nodes, edges = _build(steps, **variant)
+    hb = _closure(nodes, edges)
+    ns = len(steps)
+
+    def plane_reads(n):
+        if n[0] != "M":
+            return set()
+        _, b, s, t = n
+        return {(p, r) for p, sh in steps[s]["reads"] for r in range(128 * t + sh, 128 * t + sh + 128)}
+
+    def plane_writes(n):
+        if n[0] == "S":
+            return {(0, r) for r in range(128 * TILES)}       # plane 0, every row (each group: interleaved rows)
+        if n[0] == "E":
+            _, b, s, t = n
+            return {(p, r) for p in steps[s]["writes"] for r in range(128 * t, 128 * t + 128)}
+        return set()
+
+    acc_w = {n: n[3] for n in nodes if n[0] == "M"}
+    acc_r = {n: n[3] for n in nodes if n[0] == "E"}
+    pr = {n: plane_reads(n) for n in nodes}
+    pw = {n: plane_writes(n) for n in nodes}
+    races = []
+    for u, v in itertools.combinations(nodes, 2):
+        conflict = bool(pw[u] & (pr[v] | pw[v])) or bool(pw[v] & pr[u])
+        if u[0] == "S" and v[0] == "S" and u[1] == v[1]:
+            conflict = False                                   # the groups of one staging write disjoint rows
+        if not conflict and ((u in acc_w and v in acc_r) or (u in acc_r and v in acc_w)):
+            conflict = acc_w.get(u, acc_r.get(u)) == acc_w.get(v, acc_r.get(v))
+        if not conflict and u in acc_w and v in acc_w:
+            conflict = acc_w[u] == acc_w[v]
+        if conflict and not hb(u, v) and not hb(v, u):
+            races.append((u, v))
+    return races
+
+
+@pytest.mark.parametrize("name", ["FullyCNN", "FullyCNNV2", "FullyCNNV3"])
+def test_protocol_orders_every_conflicting_access(name):
+    steps = _accesses(name)
+    assert _races(steps) == []
+
+
+def test_model_detects_the_known_protocol_bugs():
+    """The checker is not vacuous: each weakened protocol has races."""
+    steps = _accesses("FullyCNNV2")
+    r = _races(steps, wait_prev_tile=False)                   # the two-commit wait (tile t-1's MMAs read tile t's halo)
+    assert any(u[0] != v[0] and {u[0], v[0]} == {"M", "E"} for u, v in r)
+    assert _races(steps, scout_waits_final_epilogue=False)    # next batch's first layer overwrites unread accumulators
+    assert _races(steps, stage_waits_final_done=False)        # staging plane 0 under the output layer's MMAs
