@@ -3,13 +3,15 @@
 The kernel (csrc/rced_net_tc.cu) updates its activation planes in place while MMAs of neighbouring row
 tiles, of the next layer and of the next batch are in flight; what keeps that safe is a handful of waits
 (the three commits an epilogue awaits, the scout's cumulative act_ready waits, final_done before the next
-batch is staged, in_ready before its first layer).  This test rebuilds those waits as a graph over the
-events of two consecutive batches -- M(b,s,t): the MMAs of (step, row tile); E(b,s,t): its epilogue;
-S(b,g): epilogue group g staging batch b's input -- takes the rows and planes every event reads and
-writes from the library's own layout tables (rced_tc_layout), and asserts that every pair of conflicting
-accesses (plane write vs plane read or write on overlapping rows; accumulator write vs read) is ordered
-by the transitive closure.  It would have caught the race of the two-commit wait with three issuing
-threads (tile t-1's MMAs not awaited), which the GPU tests passed."""
+batch is staged, in_ready before its first layer, w_free / w_full of the weight double buffer).  This test
+rebuilds those waits as a graph over the events of two consecutive batches -- M(b,s,t): the MMAs of (step,
+row tile); E(b,s,t): its epilogue; S(b,g): epilogue group g staging batch b's input; W(b,s): the producer's
+copy of step s's weights -- takes the rows and planes every event reads and writes from the library's own
+layout tables (rced_tc_layout), and asserts that every pair of conflicting accesses (plane write vs plane
+read or write on overlapping rows; accumulator write vs read; weight buffer write vs read) is ordered by
+the transitive closure.  It would have caught the race of the two-commit wait with three issuing threads
+(tile t-1's MMAs not awaited), which the GPU tests passed.  Not modelled: the skip scratch (written and
+read by the same thread), the output partial sums and the input double buffer (bar.sync / counters)."""
 import itertools
 
 import pytest
@@ -52,7 +54,8 @@ def _accesses(name):
     return steps
 
 
-def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_waits_final_done=True):
+def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_waits_final_done=True,
+           producer_waits_w_free=True):
     ns = len(steps)
     nodes, edges = [], {}
 
@@ -101,6 +104,22 @@ def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_wa
                 seq = [("E", 0, ns - 1, g + GROUPS)] + seq
             for u, v in zip(seq[:-1], seq[1:]):
                 before(u, v)
+    # weight producer: W(b,s) copies step s's tiles into buffer s & 1 once the step two before has released it
+    # (w_free: a commit of every issuing thread behind its last tile of that step); the scout waits for w_full
+    # before it clears the step's first tile, and clears the tiles in order
+    for b in range(2):
+        for s in range(ns):
+            node("W", b, s)
+            k = b * ns + s
+            if k >= 2 and producer_waits_w_free:
+                pb, ps = divmod(k - 2, ns)
+                for t in range(TILES):
+                    before(("M", pb, ps, t), ("W", b, s))
+            if k >= 1:                                        # one producer thread, in step order
+                pb, ps = divmod(k - 1, ns)
+                before(("W", pb, ps), ("W", b, s))
+            for t in range(TILES):
+                before(("W", b, s), ("M", b, s, t))
     if stage_waits_final_done:                                # final_done: every MMA of the output layer
         for g in range(GROUPS):
             for t in range(TILES):
@@ -166,6 +185,8 @@ def _races(steps, **variant):
             conflict = acc_w.get(u, acc_r.get(u)) == acc_w.get(v, acc_r.get(v))
         if not conflict and u in acc_w and v in acc_w:
             conflict = acc_w[u] == acc_w[v]
+        if not conflict and "W" in (u[0], v[0]) and {u[0], v[0]} <= {"W", "M"}:
+            conflict = (u[1] * ns + u[2]) % 2 == (v[1] * ns + v[2]) % 2   # same weight buffer (write vs read, write vs write)
         if conflict and not hb(u, v) and not hb(v, u):
             races.append((u, v))
     return races
@@ -184,3 +205,4 @@ def test_model_detects_the_known_protocol_bugs():
     assert any(u[0] != v[0] and {u[0], v[0]} == {"M", "E"} for u, v in r)
     assert _races(steps, scout_waits_final_epilogue=False)    # next batch's first layer overwrites unread accumulators
     assert _races(steps, stage_waits_final_done=False)        # staging plane 0 under the output layer's MMAs
+    assert _races(steps, producer_waits_w_free=False)         # weights of step s+2 land under the MMAs of step s
