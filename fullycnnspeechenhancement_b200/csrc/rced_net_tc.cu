@@ -204,7 +204,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     return pol;
 }
 __device__ __forceinline__ float4 ld_hint4(const float4* p, uint64_t pol) {
-#if RCED_TC_SKIPHINT
+#if RCED_TC_SKIPHINT == 3   // untested candidate (round 2): skip rows are read once -- keep them out of the L1
+    (void)pol;
+    return __ldcg(p);
+#elif RCED_TC_SKIPHINT
     float4 v;
     asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
@@ -216,7 +219,10 @@ __device__ __forceinline__ float4 ld_hint4(const float4* p, uint64_t pol) {
 #endif
 }
 __device__ __forceinline__ void st_hint4(float4* p, const float4 v, uint64_t pol) {
-#if RCED_TC_SKIPHINT
+#if RCED_TC_SKIPHINT == 3
+    (void)pol;
+    __stcg(p, v);
+#elif RCED_TC_SKIPHINT
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
                  : "memory");
 #else
@@ -224,7 +230,7 @@ __device__ __forceinline__ void st_hint4(float4* p, const float4 v, uint64_t pol
 #endif
 }
 __device__ __forceinline__ void st_hint1(float* p, const float v, uint64_t pol) {
-#if RCED_TC_SKIPHINT
+#if RCED_TC_SKIPHINT == 1 || RCED_TC_SKIPHINT == 2
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 #else
     *p = v;
@@ -597,7 +603,9 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         if (elect_one()) {
             const uint32_t flag = bars + 8 * kFlagSlot;
             uint32_t seen = 0;   // last value read from the scout's counter
+#if RCED_TC_MAXINFLIGHT > 0
             uint32_t issued_seen = 0;   // last value read from the count of tiles whose issue is complete
+#endif
             const uint32_t a16_0 = smem_u32(act) >> 4;                                   // plane 0, in 16-byte units
             const uint32_t w16_0 = smem_u32(smem + smem_w_off(ARCH, 0)) >> 4;            // weight buffer 0
             const uint32_t w16_step = (uint32_t)(smem_w_off(ARCH, 1) - smem_w_off(ARCH, 0)) >> 4;
