@@ -29,7 +29,14 @@ def main(rep, bucket=256):
             "sass__inst_executed_shared_loads", "sm__cycles_elapsed.avg.per_second",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-            "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed"]
+            "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed",
+            # the units that bind the tensor-core kernel and K1 / K3
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+            "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+            "smsp__inst_executed.sum"]
     for h, u, v in zip(hdr, units, vals):
         if h in want or ("issue_stalled" in h and h.endswith("per_issue_active.ratio") and float(v or 0) > 0.004):
             print("%s [%s] = %s" % (h, u, v))
