@@ -38,7 +38,8 @@ def test_sass_is_blackwell_native():
     if not out:
         pytest.skip("cuobjdump not available")
     assert "sm_100a" in out
-    for mnemonic in ("STTM", "LDTM", "UBLKCP", "FFMA"):
+    # tensor-memory store / load, bulk async copy, FP32 FMA, tcgen05.mma and its commit, uniform constant loads
+    for mnemonic in ("STTM", "LDTM", "UBLKCP", "FFMA", "UTCHMMA", "UTCBAR", "LDCU"):
         assert mnemonic in out, mnemonic
 
 
