@@ -53,8 +53,15 @@ SIGNATURES = {
 }
 
 
+ERR_ARG, ERR_CUDA, ERR_STATE = -1, -2, -3
+
+
 class RcedError(RuntimeError):
-    pass
+    """`code` is the library's return value (ERR_ARG / ERR_CUDA / ERR_STATE), None for loader errors."""
+
+    def __init__(self, message, code=None):
+        RuntimeError.__init__(self, message)
+        self.code = code
 
 
 _lib = None
@@ -81,7 +88,7 @@ def lib():
 
 def check(code):
     if code != 0:
-        raise RcedError("librced_b200 error %d: %s" % (code, lib().rced_last_error().decode("utf-8", "replace")))
+        raise RcedError("librced_b200 error %d: %s" % (code, lib().rced_last_error().decode("utf-8", "replace")), code)
 
 
 def num_frames(n_samples):

@@ -6,7 +6,6 @@
 #include <string.h>
 
 #include <atomic>
-#include <map>
 #include <string>
 #include <vector>
 
@@ -233,27 +232,33 @@ static void pack_weights(int arch, const float* folded, float* packed) {
 
 using namespace rced;
 
+constexpr unsigned int kFlagRing = 4096;   // guard-flag pairs handed out round robin, one per tensor-core launch
+
 struct rced_handle {
     int arch;
     int device;
     int num_sms;
     bool skip_in_tmem;
     float* d_packed;
+    // FFMA kernel with skips in global memory (rced_set_skip_in_tmem(h, 0)): num_sms regions + claim words
     float* d_scratch;
+    unsigned int* d_scratch_busy;
     // tensor-core variant (rced_net_tc.cu), allocated by rced_set_variant(h, RCED_VARIANT_TC)
     int variant;
     std::vector<float> folded;
     unsigned char* d_tc_img;
     float* d_tc_bias;
-    // The tensor-core kernel parks skip tensors in a per-CTA global scratch and reports through a
-    // flag word; launches on different streams may overlap, so each stream gets its own pair
-    // (allocated on the stream's first launch).
-    struct TcStream {
-        float* skip;
-        unsigned int* flags;
-    };
-    std::map<void*, TcStream> tc_streams;
-    unsigned int* last_tc_flags;
+    // The tensor-core kernel parks skip tensors in a global scratch of num_sms regions; a CTA claims a
+    // region when it starts (rced_slots.cuh), so launches that overlap on different streams share the
+    // one scratch.  Every launch reports through its own pair of guard-flag words, taken round robin
+    // from a ring (stream-ordered memset in front of the launch; a pair is reused after kFlagRing launches).
+    float* d_tc_skip;
+    unsigned int* d_tc_busy;
+    unsigned int* d_tc_flags;
+    std::atomic<unsigned int> tc_launches;
+    std::atomic<unsigned int*> last_tc_flags;
+    size_t tc_persist_bytes;       // > 0: launches carry an L2 access-policy window over the scratch
+    const char* trace_path;        // RCED_TC_TRACE (development aid), read once
 };
 
 struct DeviceGuard {
@@ -353,11 +358,18 @@ int rced_create(int arch, const float* folded, size_t n_folded, int device, rced
     h->skip_in_tmem = true;
     h->d_packed = nullptr;
     h->d_scratch = nullptr;
+    h->d_scratch_busy = nullptr;
     h->variant = RCED_VARIANT_FFMA;
     h->folded.assign(folded, folded + n_folded);
     h->d_tc_img = nullptr;
     h->d_tc_bias = nullptr;
+    h->d_tc_skip = nullptr;
+    h->d_tc_busy = nullptr;
+    h->d_tc_flags = nullptr;
+    h->tc_launches = 0;
     h->last_tc_flags = nullptr;
+    h->tc_persist_bytes = 0;
+    h->trace_path = getenv("RCED_TC_TRACE");
     if ((e = cudaMalloc(&h->d_packed, packed.size() * sizeof(float))) != cudaSuccess) {
         delete h;
         return cuda_fail(e, "cudaMalloc(weights)");
@@ -376,12 +388,12 @@ void rced_destroy(rced_handle* h) {
     DeviceGuard guard(h->device);
     if (h->d_packed) cudaFree(h->d_packed);
     if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_scratch_busy) cudaFree(h->d_scratch_busy);
     if (h->d_tc_img) cudaFree(h->d_tc_img);
     if (h->d_tc_bias) cudaFree(h->d_tc_bias);
-    for (auto& kv : h->tc_streams) {
-        cudaFree(kv.second.skip);
-        cudaFree(kv.second.flags);
-    }
+    if (h->d_tc_skip) cudaFree(h->d_tc_skip);
+    if (h->d_tc_busy) cudaFree(h->d_tc_busy);
+    if (h->d_tc_flags) cudaFree(h->d_tc_flags);
     delete h;
 }
 
@@ -393,8 +405,18 @@ int rced_set_skip_in_tmem(rced_handle* h, int enable) {
     if (!enable && !h->d_scratch) {
         DeviceGuard guard(h->device);
         const size_t bytes = (size_t)h->num_sms * kFramesPerCta * 512 * 32 * sizeof(float);
-        cudaError_t e = cudaMalloc(&h->d_scratch, bytes);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(skip scratch)");
+        float* scratch = nullptr;
+        unsigned int* busy = nullptr;
+        cudaError_t e = cudaMalloc(&scratch, bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&busy, (size_t)h->num_sms * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMemset(busy, 0, (size_t)h->num_sms * sizeof(unsigned int));
+        if (e != cudaSuccess) {
+            cudaFree(scratch);
+            cudaFree(busy);
+            return cuda_fail(e, "cudaMalloc(skip scratch)");
+        }
+        h->d_scratch = scratch;
+        h->d_scratch_busy = busy;
     }
     h->skip_in_tmem = enable != 0;
     return RCED_OK;
@@ -453,18 +475,57 @@ int rced_set_variant(rced_handle* h, int variant) {
     if (!h) return fail(RCED_ERR_ARG, "null handle");
     if (variant != RCED_VARIANT_FFMA && variant != RCED_VARIANT_TC) return fail(RCED_ERR_ARG, "unknown variant");
     if (variant == RCED_VARIANT_TC && !h->d_tc_img) {
+        // weights of any finite magnitude are fine (every step's weights are scaled by a power of two)
         for (float w : h->folded)
-            if (!(fabsf(w) <= 65504.f)) return fail(RCED_ERR_STATE, "a folded weight exceeds the FP16 range: tensor-core variant refused");
+            if (!isfinite(w)) return fail(RCED_ERR_STATE, "a folded weight is not finite: tensor-core variant refused");
         DeviceGuard guard(h->device);
         std::vector<unsigned char> img((size_t)tc_image_bytes(h->arch));
         std::vector<float> bias((size_t)tc_bias_floats(h->arch));
         tc_pack_weights(h->arch, h->folded.data(), img.data(), bias.data());
-        cudaError_t e;
-        if ((e = cudaMalloc(&h->d_tc_img, img.size())) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc image)");
-        if ((e = cudaMalloc(&h->d_tc_bias, bias.size() * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc bias)");
-        if ((e = cudaMemcpy(h->d_tc_img, img.data(), img.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tc image)");
-        if ((e = cudaMemcpy(h->d_tc_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
-            return cuda_fail(e, "cudaMemcpy(tc bias)");
+        // all-or-nothing: the handle only sees the buffers when every allocation and upload succeeded
+        unsigned char* d_img = nullptr;
+        float *d_bias = nullptr, *d_skip = nullptr;
+        unsigned int *d_busy = nullptr, *d_flags = nullptr;
+        const size_t skip_bytes = (size_t)h->num_sms * tc_skip_floats_per_cta(h->arch) * sizeof(float);
+        const char* what = "cudaMalloc(tc image)";
+        cudaError_t e = cudaMalloc(&d_img, img.size());
+        if (e == cudaSuccess) { what = "cudaMalloc(tc bias)"; e = cudaMalloc(&d_bias, bias.size() * sizeof(float)); }
+        if (e == cudaSuccess) { what = "cudaMalloc(tc skip scratch)"; e = cudaMalloc(&d_skip, skip_bytes); }
+        if (e == cudaSuccess) { what = "cudaMalloc(tc claim words)"; e = cudaMalloc(&d_busy, (size_t)h->num_sms * sizeof(unsigned int)); }
+        if (e == cudaSuccess) { what = "cudaMalloc(tc flags)"; e = cudaMalloc(&d_flags, (size_t)kFlagRing * 2 * sizeof(unsigned int)); }
+        if (e == cudaSuccess) { what = "cudaMemset(tc claim words)"; e = cudaMemset(d_busy, 0, (size_t)h->num_sms * sizeof(unsigned int)); }
+        if (e == cudaSuccess) { what = "cudaMemset(tc flags)"; e = cudaMemset(d_flags, 0, (size_t)kFlagRing * 2 * sizeof(unsigned int)); }
+        if (e == cudaSuccess) { what = "cudaMemcpy(tc image)"; e = cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice); }
+        if (e == cudaSuccess) { what = "cudaMemcpy(tc bias)"; e = cudaMemcpy(d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice); }
+        if (e != cudaSuccess) {
+            cudaFree(d_img);
+            cudaFree(d_bias);
+            cudaFree(d_skip);
+            cudaFree(d_busy);
+            cudaFree(d_flags);
+            return cuda_fail(e, what);
+        }
+        h->d_tc_img = d_img;
+        h->d_tc_bias = d_bias;
+        h->d_tc_skip = d_skip;
+        h->d_tc_busy = d_busy;
+        h->d_tc_flags = d_flags;
+        // Optional (RCED_TC_L2_PERSIST=1, measured in DESIGN.md): set aside L2 for persisting lines and mark the
+        // scratch with an access-policy window on every launch.
+        const char* pers = getenv("RCED_TC_L2_PERSIST");
+        if (pers && atoi(pers) > 0) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                size_t want = skip_bytes;
+                if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                    size_t win = skip_bytes;
+                    if (prop.accessPolicyMaxWindowSize > 0 && win > (size_t)prop.accessPolicyMaxWindowSize)
+                        win = (size_t)prop.accessPolicyMaxWindowSize;
+                    h->tc_persist_bytes = win;
+                }
+            }
+        }
     }
     h->variant = variant;
     return RCED_OK;
@@ -472,10 +533,13 @@ int rced_set_variant(rced_handle* h, int variant) {
 int rced_variant(const rced_handle* h) { return h ? h->variant : -1; }
 int rced_tc_status(rced_handle* h, float* max_abs, unsigned int* protocol_error) {
     if (!h) return fail(RCED_ERR_ARG, "null handle");
-    if (!h->last_tc_flags) return fail(RCED_ERR_STATE, "the tensor-core kernel has not been launched on this handle");
+    unsigned int* last = h->last_tc_flags.load();
+    if (!last) return fail(RCED_ERR_STATE, "the tensor-core kernel has not been launched on this handle");
     DeviceGuard guard(h->device);
     unsigned int f[2];
-    cudaError_t e = cudaMemcpy(f, h->last_tc_flags, sizeof(f), cudaMemcpyDeviceToHost);
+    // every stream, blocking or not, has finished before the flags are read
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(f, last, sizeof(f), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tc flags)");
     if (max_abs) memcpy(max_abs, &f[0], 4);
     if (protocol_error) *protocol_error = f[1];
@@ -518,39 +582,30 @@ int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n
     p.n_utt = n_utt;
     p.total_rows = total_rows;
     p.skip_scratch = h->d_scratch;
+    p.slot_busy = h->d_scratch_busy;
+    p.n_slots = h->num_sms;
     p.guard = nullptr;
     cudaError_t e;
     if (h->variant == RCED_VARIANT_TC) {
         // tensor-core kernel first; the FP32 FFMA kernel follows on the same stream and returns at
-        // once unless the range guard tripped (an activation beyond the FP16 range) or the
-        // tensor-core kernel reported a protocol error -- stream-ordered, no host synchronisation
-        auto it = h->tc_streams.find(stream);
-        if (it == h->tc_streams.end()) {
-            rced_handle::TcStream ts{nullptr, nullptr};
-            const size_t skip_bytes = (size_t)h->num_sms * tc_skip_floats_per_cta(h->arch) * sizeof(float);
-            if ((e = cudaMalloc(&ts.skip, skip_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tc skip scratch)");
-            if ((e = cudaMalloc(&ts.flags, 2 * sizeof(unsigned int))) != cudaSuccess) {
-                cudaFree(ts.skip);
-                return cuda_fail(e, "cudaMalloc(tc flags)");
-            }
-            it = h->tc_streams.emplace(stream, ts).first;
-        }
-        float* const d_skip = it->second.skip;
-        unsigned int* const d_flags = it->second.flags;
-        h->last_tc_flags = d_flags;
+        // once unless the range guard tripped (an activation beyond the FP16 range, an input that is
+        // not finite) or the tensor-core kernel reported a protocol error -- stream-ordered, no host
+        // synchronisation
+        unsigned int* const d_flags = h->d_tc_flags + 2 * (size_t)(h->tc_launches.fetch_add(1) % kFlagRing);
+        h->last_tc_flags.store(d_flags);
         if ((e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream)) != cudaSuccess)
             return cuda_fail(e, "cudaMemsetAsync(tc flags)");
         // development aid: RCED_TC_TRACE=<file> dumps clock64 stamps of CTA 0's second batch (synchronises)
-        const char* trace_path = getenv("RCED_TC_TRACE");
         long long* d_trace = nullptr;
         const int slots = tc_trace_slots(h->arch);
-        if (trace_path && cudaMalloc(&d_trace, slots * sizeof(long long)) == cudaSuccess) cudaMemset(d_trace, 0, slots * sizeof(long long));
-        e = launch_net_tc(h->arch, p, h->d_tc_img, h->d_tc_bias, d_skip, d_flags, d_trace, h->num_sms, (cudaStream_t)stream);
+        if (h->trace_path && cudaMalloc(&d_trace, slots * sizeof(long long)) == cudaSuccess) cudaMemset(d_trace, 0, slots * sizeof(long long));
+        e = launch_net_tc(h->arch, p, h->d_tc_img, h->d_tc_bias, h->d_tc_skip, h->d_tc_busy, h->num_sms, h->tc_persist_bytes,
+                          d_flags, d_trace, h->num_sms, (cudaStream_t)stream);
         count_launch();
         if (d_trace) {
             std::vector<long long> t(slots);
             if (cudaMemcpy(t.data(), d_trace, slots * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
-                if (FILE* f = fopen(trace_path, "w")) {
+                if (FILE* f = fopen(h->trace_path, "w")) {
                     for (int i = 0; i < slots; ++i) fprintf(f, "%lld%c", t[i], (i + 1) % tc::kTraceEvents == 0 ? '\n' : ' ');
                     fclose(f);
                 }

@@ -13,7 +13,10 @@ struct NetParams {
     const long long* row_off;   // [n_utt + 1]
     int n_utt;
     long long total_rows;
-    float* skip_scratch;        // only read when skips are not parked in tensor memory
+    float* skip_scratch;        // only used when skips are not parked in tensor memory: n_slots regions of
+                                // kFramesPerCta * 512 * 32 floats and their claim words (rced_slots.cuh)
+    unsigned int* slot_busy;
+    int n_slots;
     // When not null: flags written by the tensor-core kernel that ran before on the same stream
     // ([0] bits of the largest |activation| it stored as FP16, [1] protocol error).  The FFMA
     // kernel then only runs (and overwrites `out`) if the FP16 range was exceeded or an error
@@ -53,8 +56,11 @@ size_t tc_skip_floats_per_cta(int arch);
 int tc_smem_bytes(int arch);
 void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* bias);
 int tc_trace_slots(int arch);
+// skip: n_slots regions of tc_skip_floats_per_cta floats, slot_busy: their claim words (zero-initialised);
+// persist_bytes > 0: the launch carries an L2 access-policy window (persisting) over the first persist_bytes of skip
 cudaError_t launch_net_tc(int arch, const NetParams& p, const unsigned char* wimg, const float* bias, float* skip,
-                          unsigned int* flags, long long* trace, int num_sms, cudaStream_t stream);
+                          unsigned int* slot_busy, int n_slots, size_t persist_bytes, unsigned int* flags, long long* trace,
+                          int num_sms, cudaStream_t stream);
 cudaError_t launch_stft(const StftParams& p, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, long long max_rows_per_utt, cudaStream_t stream);
 cudaError_t upload_tables_stft();    // twiddles + window tables of K1 -> current device

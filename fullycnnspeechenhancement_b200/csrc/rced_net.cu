@@ -29,6 +29,7 @@
 
 #include "rced_arch.cuh"
 #include "rced_internal.h"
+#include "rced_slots.cuh"
 
 namespace rced {
 
@@ -511,6 +512,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
     float* slots = smem + pad4(PK);
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_tmem;
+    __shared__ int s_slot;
 
     // fall-back role behind the tensor-core variant: nothing to do unless its guard tripped
     if (p.guard != nullptr && p.guard[0] <= 0x477FE000u /* 65504.0f */ && p.guard[1] == 0u) return;
@@ -550,8 +552,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
         tmem_fence_after();
         sk.base = s_tmem + ((uint32_t)fs << 21);   // lane field (bits 31:16) = 32 * (warp % 4)
     } else {
-        sk.base = p.skip_scratch + ((size_t)blockIdx.x * kFramesPerCta + fs) * (512 * 32) + lane;
+        // launches of one handle may overlap (several streams): the CTA claims a region of the scratch
+        if (threadIdx.x == 0) s_slot = scratch_slot_acquire(p.slot_busy, p.n_slots);
         __syncthreads();
+        if (s_slot < 0) __trap();   // every region busy: a kernel was killed between claim and release
+        sk.base = p.skip_scratch + ((size_t)s_slot * kFramesPerCta + fs) * (512 * 32) + lane;
     }
     mbar_wait(bar, 0);
 
@@ -575,6 +580,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) rced_net_kernel(const Ne
         tmem_fence_before();
         __syncthreads();
         if (warp == 0) tmem_dealloc512(s_tmem);
+    } else {
+        __syncthreads();
+        if (threadIdx.x == 0) scratch_slot_release(p.slot_busy, s_slot);
     }
 }
 

@@ -13,7 +13,10 @@
 //    chunks, the A descriptor of a tap being the activation plane shifted by (tap - pad) rows;
 //  * FP32 accuracy from FP16 tensor cores by an error-compensated split: activations and
 //    weights are stored as hi + lo FP16 pairs and every K step issues A_hi x [Whi | Wlo]
-//    (N = 2 NP) and A_lo x Whi (N = NP) into FP32 accumulators in tensor memory;
+//    (N = 2 NP) and A_lo x Whi (N = NP) into FP32 accumulators in tensor memory.  The residuals are
+//    stored times 2^11, the weights of a step times a power of two and every frame in its own
+//    power-of-two scaled domain (rced_tc.cuh, "Range"), so that the FP16 operands stay in their normal
+//    range for inputs and weights of any magnitude;
 //  * warp roles (rced_tc.cuh): warps 0, 3, 5 issue the MMAs (one elected lane each, row tiles of the
 //    global (step, tile) sequence round robin, all descriptor arithmetic in the uniform datapath from
 //    constant-memory tables), warp 1 streams the next layers' weight tiles from L2 with bulk async
@@ -30,9 +33,11 @@
 //    sum_n E[b + n][n] with one shuffle per column (fixed order).  The shifts would reach the
 //    neighbouring frames, so the last conv layer writes an even-frames-only and an odd-frames-only
 //    copy of its output and each parity has its own accumulator columns;
-//  * skip tensors go to a per-CTA FP32 scratch in global memory (L2 resident);
+//  * skip tensors go to a per-CTA FP32 scratch in global memory (L2 resident), written after the
+//    epilogue has released its row tile (the values are read back from the planes);
 //  * range guard: FP16 overflows beyond 65504.  The kernel records the largest |activation| it
-//    stored; rced_forward re-runs the batch with the FP32 FFMA kernel when the guard tripped.
+//    stored (in the frames' scaled domains) and whether an input was not finite; rced_forward
+//    re-runs the call with the FP32 FFMA kernel when the guard tripped.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -41,6 +46,7 @@
 #include <vector>
 
 #include "rced_internal.h"
+#include "rced_slots.cuh"
 #include "rced_tc.cuh"
 
 namespace rced {
@@ -245,22 +251,58 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo) { return ((uint64_t)k
 // instruction descriptor: FP16 A/B (format 0), FP32 accumulate, both K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
 
-// x = hi + lo as two FP16 pairs; element a goes to the low half
+// x = hi + 2^-11 lo as two FP16 pairs (the residual is stored times 2^11: it has the magnitude of x
+// itself and stays a normal FP16 number whenever hi is one); element a goes to the low half
+constexpr float kLoScale = (float)(1 << kLoShift), kLoInv = 1.f / (float)(1 << kLoShift);
+// packed FP32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): the epilogue is bound by its issue slots, and
+// a packed instruction does the work of two
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    float ra, rb;
+    unpack2(mul2(sub2(pack2(a, b), pack2(hf.x, hf.y)), pack2(kLoScale, kLoScale)), ra, rb);
+    const __half2 l = __floats2half2_rn(ra, rb);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// largest |value| of the packed FP16 pairs seen so far (the range guard: an overflow is an infinity here)
+__device__ __forceinline__ void track_max(uint32_t& amax2, uint32_t h) {
+    asm("{\n\t.reg .b32 t;\n\tabs.f16x2 t, %1;\n\tmax.f16x2 %0, %0, t;\n\t}" : "+r"(amax2) : "r"(h));
+}
 // rows that are not (frame, bin) rows of the batch -- the halo rows between frames and everything
 // behind the last frame -- are stored as zeros whatever was computed for them
-__device__ __forceinline__ void store_split8(unsigned char* act, int cg, int q, const float (&v)[8], bool valid) {
+__device__ __forceinline__ void store_split8(unsigned char* act, int cg, int q, const float (&v)[8], bool valid, uint32_t& amax2) {
     uint4 h, l;
     split2(v[0], v[1], h.x, l.x);
     split2(v[2], v[3], h.y, l.y);
     split2(v[4], v[5], h.z, l.z);
     split2(v[6], v[7], h.w, l.w);
+    track_max(amax2, h.x);
+    track_max(amax2, h.y);
+    track_max(amax2, h.z);
+    track_max(amax2, h.w);
     uint4* ph = reinterpret_cast<uint4*>(act) + cg * kPlane16 + q;
     if (valid) {
         ph[0] = h;
@@ -273,12 +315,17 @@ __device__ __forceinline__ void store_split8(unsigned char* act, int cg, int q, 
 
 // The last conv layer feeds the row-shifted output layer: its rows are stored twice, in planes
 // (0, 1) if the row's frame index is even and in planes (2, 3) if it is odd, zeros in the other pair
-__device__ __forceinline__ void store_split8_parity(unsigned char* act, int cg, int q, const float (&v)[8], bool valid, int odd) {
+__device__ __forceinline__ void store_split8_parity(unsigned char* act, int cg, int q, const float (&v)[8], bool valid, int odd,
+                                                    uint32_t& amax2) {
     uint4 h, l;
     split2(v[0], v[1], h.x, l.x);
     split2(v[2], v[3], h.y, l.y);
     split2(v[4], v[5], h.z, l.z);
     split2(v[6], v[7], h.w, l.w);
+    track_max(amax2, h.x);
+    track_max(amax2, h.y);
+    track_max(amax2, h.z);
+    track_max(amax2, h.w);
     if (!valid) h = l = make_uint4(0, 0, 0, 0);
     uint4* pe = reinterpret_cast<uint4*>(act) + cg * kPlane16 + q;   // even-frame copy
     uint4* po = pe + 2 * kPlane16;                                   // odd-frame copy
@@ -316,14 +363,16 @@ __constant__ IssueTab<ARCH> c_issue = IssueTab<ARCH>();
 
 struct TcParams {
     const unsigned char* wimg;   // weight image (global): per step, per unit, [2][rows][8] halfs
-    const float* bias;           // [n_steps][32]
+    const float* bias;           // [n_steps + 1][32]: biases per step, then the steps' c1 and the largest |bias| (rced_tc.cuh)
     const float* in;             // mag  [total_rows][129]
     float* out;                  // pred [total_rows][129]
     const long long* row_off;    // [n_utt + 1]
     int n_utt;
     long long total_rows;
-    float* skip;                 // per-CTA scratch for the skip tensors
-    unsigned int* flags;         // [0] bits of the largest |activation| stored as FP16, [1] protocol error
+    float* skip;                 // scratch for the skip tensors: n_slots regions of skip_floats_per_cta
+    unsigned int* slot_busy;     // [n_slots] claim words of the regions (rced_slots.cuh)
+    int n_slots;
+    unsigned int* flags;         // [0] bits of the largest |activation| stored as FP16 (scaled domain; >= inf: an input was not finite), [1] protocol error
     long long* trace;            // development aid (RCED_TC_TRACE): clock64 stamps of CTA 0's second batch, or null
 };
 // trace slots: [step][tile][event]; events: 0 MMA issue begins, 1 MMA issued (commit), 2 epilogue
@@ -344,7 +393,7 @@ struct EpiStep {
     int add_base;  // first 8-channel group of the skip slot added
     int save_base; // first 8-channel group of the skip slot saved (-1: none)
     int last;      // the last conv layer: even / odd frame copies for the output layer
-    int pad1;
+    float skip_r;  // power of two between the domain of the skip tensor added and this step's domain
 };
 static_assert(sizeof(EpiStep) == 32, "EpiStep layout");
 
@@ -354,6 +403,7 @@ struct Ctx {
     uint32_t bars;      // shared address of the barrier block
     uint32_t tm;        // tensor-memory base
     const float* bias;  // shared copy
+    const float* scale; // power-of-two scales of the batch's frames ([8], shared; written by the prefetch warp)
     const EpiStep* epi; // shared copy
     const long long* bnd;
     unsigned int* err;
@@ -382,7 +432,7 @@ __device__ __forceinline__ void locate(const long long* __restrict__ row_off, in
 // ------------------------------------------------------------------------------------------
 // epilogue of one conv layer for one row tile (runtime-parameterised, see EpiStep)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const int t, const uint32_t par, float& amax) {
+__device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const int t, const uint32_t par, uint32_t& amax2) {
     EpiStep e = c.epi[s];
 #ifdef RCED_TC_DIAG_NOSKIP   // diagnosis only (wrong results): no skip traffic
     e.add = 0;
@@ -397,6 +447,8 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
     const int r = t * 128 + c.quad * 32 + c.lane;   // row in tile space
     const int fi = r / kFS, b = r - fi * kFS;
     const bool valid = fi < c.nf && b < kBins;
+    const float sf = c.scale[fi];                    // the frame's scale: the (pre-scaled) biases enter its domain times sf
+    const u64 sf2 = pack2(sf, sf), loinv2 = pack2(kLoInv, kLoInv), r2 = pack2(e.skip_r, e.skip_r);
     const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
     // Skip tensors: FP32 in a per-CTA global scratch (L2), [group of 8 channels][half][row][4 floats], so
     // that a warp's 16-byte accesses cover whole sectors.  The row is saved and added by the same thread.
@@ -443,13 +495,23 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
         const float ss[8] = {sk0.x, sk0.y, sk0.z, sk0.w, sk1.x, sk1.y, sk1.z, sk1.w};
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float x = (d1[i] + d2[i]) + bb[i];
-            if (e.add == 1) x += ss[i];
-            if (e.relu) x = fmaxf(x, 0.f);
-            if (e.add == 2) x += ss[i];
-            amax = fmaxf(amax, fabsf(x));   // (halo rows hold finite sums of their neighbours: harmless)
-            v[i] = x;
+        for (int i = 0; i < 4; ++i) {
+            // hi*Whi + 2^-11 (hi*Wlo' + lo'*Whi) + bias, two channels per instruction
+            u64 x = fma2(pack2(d2[2 * i], d2[2 * i + 1]), loinv2, pack2(d1[2 * i], d1[2 * i + 1]));
+            x = fma2(pack2(bb[2 * i], bb[2 * i + 1]), sf2, x);
+            if (e.add == 1) x = fma2(pack2(ss[2 * i], ss[2 * i + 1]), r2, x);
+            float xa, xb;
+            unpack2(x, xa, xb);
+            if (e.relu) {
+                xa = fmaxf(xa, 0.f);
+                xb = fmaxf(xb, 0.f);
+            }
+            if (e.add == 2) {
+                xa = fmaf(ss[2 * i], e.skip_r, xa);
+                xb = fmaf(ss[2 * i + 1], e.skip_r, xb);
+            }
+            v[2 * i] = xa;       // (the range guard looks at the FP16 values stored below; halo rows hold
+            v[2 * i + 1] = xb;   //  finite sums of their neighbours: harmless)
         }
         // next group: accumulator columns and skip values are in flight while this one is stored
         if (g + 1 < e.cg) {
@@ -460,18 +522,44 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
                 sk1 = ld_hint4(sp + (size_t)(g + 1) * 2 * kRows + kRows, c.pol_last);
             }
         }
+#ifndef RCED_TC_SAVE_DEFERRED   // the skip row is stored from the registers, in front of the fence
         if (do_save) {
             st_hint4(dp + (size_t)g * 2 * kRows, make_float4(v[0], v[1], v[2], v[3]), c.pol_last);
             st_hint4(dp + (size_t)g * 2 * kRows + kRows, make_float4(v[4], v[5], v[6], v[7]), c.pol_last);
         }
-        if (e.last) store_split8_parity(c.act, g, kLead + r, v, valid, fi & 1);
-        else store_split8(c.act, g, kLead + r, v, valid);
+#endif
+        if (e.last) store_split8_parity(c.act, g, kLead + r, v, valid, fi & 1, amax2);
+        else store_split8(c.act, g, kLead + r, v, valid, amax2);
     }
     fence_before();       // tcgen05.ld of this accumulator ordered before the barrier
     fence_async_smem();   // plane writes visible to the tensor core (async proxy)
     __syncwarp();
     if (c.lane == 0) mbar_arrive(bar_addr(c, kBarActReady + t));
     stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 4);
+#ifdef RCED_TC_SAVE_DEFERRED
+    // Experiment (measured slower: 14.46 against 13.92 ms, the extra instructions cost more than the MEMBAR
+    // of the proxy fence waiting for the stores): the skip tensor of the tile written AFTER the tile has
+    // been released, its values read back from the planes -- this thread's own row, which nobody overwrites
+    // before this same thread does in the next step -- as hi + 2^-11 lo.
+    if (do_save) {
+        const uint4* ph = reinterpret_cast<const uint4*>(c.act) + (kLead + r);
+#pragma unroll 1
+        for (int g = 0; g < e.cg; ++g) {
+            const uint4 h = ph[g * kPlane16], l = ph[g * kPlane16 + kLo16];
+            const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
+                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&ll[i]));
+                v[2 * i] = fmaf(lf.x, kLoInv, hf.x);
+                v[2 * i + 1] = fmaf(lf.y, kLoInv, hf.y);
+            }
+            st_hint4(dp + (size_t)g * 2 * kRows, make_float4(v[0], v[1], v[2], v[3]), c.pol_last);
+            st_hint4(dp + (size_t)g * 2 * kRows + kRows, make_float4(v[4], v[5], v[6], v[7]), c.pol_last);
+        }
+    }
+#endif
 }
 
 // Epilogue of the (1,129) layer for one row tile.  E[row r][n] (32 columns per frame parity) belongs
@@ -534,6 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     constexpr int NS = n_steps(ARCH);
     constexpr int NL = num_layers(ARCH);
     __shared__ uint32_t s_tmem;
+    __shared__ int s_slot, s_slot_owned;
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler (uniform datapath)
@@ -545,7 +634,12 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
 
     // ---- one-time setup ----------------------------------------------------------------------
     for (int i = threadIdx.x; i < (kFrontPad + kActBytes) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < NS * 32; i += kThreads) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < bias_floats(ARCH); i += kThreads) s_bias[i] = p.bias[i];
+    // frame scales of the batches in flight (ring of kScaleRing batches x 8 frames) and the row maxima of the
+    // batch being prefetched, behind the time-tap masks
+    float* s_scale = reinterpret_cast<float*>(smem + smem_bnd_off(ARCH) + 64);
+    uint32_t* s_rmax = reinterpret_cast<uint32_t*>(smem + smem_bnd_off(ARCH) + 192);
+    if (threadIdx.x < kScaleRing * 8) s_scale[threadIdx.x] = 1.f;
     EpiStep* s_epi = reinterpret_cast<EpiStep*>(smem + smem_epi_off(ARCH));
     if (threadIdx.x < NL - 1) {
         const int li = threadIdx.x;
@@ -558,8 +652,17 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         e.add_base = sp.add < 0 ? 0 : skip_c8_base(ARCH, sp.add);
         e.save_base = sp.save < 0 ? -1 : skip_c8_base(ARCH, sp.save);
         e.last = li == NL - 2 ? 1 : 0;
-        e.pad1 = 0;
+        e.skip_r = p.bias[NS * 32 + li];
         s_epi[li] = e;
+    }
+    if (threadIdx.x == 32) {   // (warp 1; warp 0 allocates the tensor memory meanwhile)
+        int slot = scratch_slot_acquire(p.slot_busy, p.n_slots);
+        s_slot_owned = slot >= 0;
+        if (slot < 0) {   // cannot happen in a healthy context: report, the FP32 kernel recomputes the call
+            atomicMax(p.flags + 1, 7u);
+            slot = (int)(blockIdx.x % (unsigned int)p.n_slots);
+        }
+        s_slot = slot;
     }
     if (threadIdx.x == 0) {
         *reinterpret_cast<volatile uint32_t*>(smem + smem_bar_off(ARCH) + 8 * kFlagSlot) = 0u;
@@ -662,8 +765,8 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                             for (int u = 0; u < nu; ++u) {
                                 const uint32_t ua = a16_0 + (uint32_t)ta[u] + toff;
                                 const uint64_t db = make_desc(ub0 + (uint32_t)u * tile16);
-                                umma_f16(d, make_desc(ua), db, id_a, u > 0);     // hi x [Whi | Wlo] -> columns [0, 2 NP)
-                                umma_f16(d, make_desc(ua + kLo16), db, id_b, 1); // lo x Whi        -> columns [0, NP)
+                                umma_f16(d, make_desc(ua), db, id_a, u > 0);            // hi x [Whi | Wlo'] -> columns [0, 2 NP)
+                                umma_f16(d + np, make_desc(ua + kLo16), db, id_b, 1);   // lo' x Whi         -> columns [NP, 2 NP): both carry 2^11
                                 if (u == 0) stamp(p.trace, tr, s, t, 6);
                             }
                         } else {
@@ -676,11 +779,12 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                                 const uint32_t po = toff + (uint32_t)(odd * 2 * kPlane16);
 #pragma unroll
                                 for (int u = 0; u < kFinalShifts; ++u) {
-                                    const uint64_t dbh = make_desc(ub0 + (uint32_t)u * tile16);                  // Whi rows 0..31
-                                    const uint64_t dbl = make_desc(ub0 + (uint32_t)u * tile16 + (uint32_t)np);   // Wlo rows 32..63
+                                    const uint64_t dbh = make_desc(ub0 + (uint32_t)u * tile16);                      // Whi        rows 0..31
+                                    const uint64_t dbl = make_desc(ub0 + (uint32_t)u * tile16 + (uint32_t)np);       // Wlo        rows 32..63
+                                    const uint64_t dbs = make_desc(ub0 + (uint32_t)u * tile16 + 2u * (uint32_t)np);  // Whi 2^-11  rows 64..95
                                     const uint32_t ua = a16_0 + (uint32_t)ta[u] + po;
                                     umma_f16(dd, make_desc(ua), dbh, id_b, u > 0);
-                                    umma_f16(dd, make_desc(ua + kLo16), dbh, id_b, 1);
+                                    umma_f16(dd, make_desc(ua + kLo16), dbs, id_b, 1);   // the activations' residual carries 2^11
                                     umma_f16(dd, make_desc(ua), dbl, id_b, 1);
                                 }
                             }
@@ -727,7 +831,8 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         float* inbuf = reinterpret_cast<float*>(smem + smem_in_off(ARCH));
         const uint32_t flag = bars + 8 * kFlagSlot;
         uint32_t itn = 0;   // local index of the batch being prefetched
-        float in_amax = 0.f;
+        const uint32_t bref = __float_as_uint(s_bias[NS * 32 + kBiasRefSlot]);   // largest |bias| (non-negative: orders like its bits)
+        bool bad_input = false;
         for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++itn) {
             if (itn >= 2) {
                 // buffer itn & 1 was read by the staging of batch itn - 2: wait until the scout has
@@ -741,11 +846,11 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             const long long g0 = batch * kFB;
             // per frame of the batch: which of its 8 time taps (rows g-3 .. g+4) lie inside its utterance
             int* tm8 = reinterpret_cast<int*>(bnd) + (itn & 1) * 8;
+            int m = 0;
             if (lane < kFB) {
                 long long lo = 0, hi = 0;
                 const long long g = g0 + lane;
                 if (g < p.total_rows) locate(p.row_off, p.n_utt, g, lo, hi);
-                int m = 0;
 #pragma unroll
                 for (int tt = 0; tt < 8; ++tt) m |= (g + tt - 3 >= lo && g + tt - 3 < hi) ? (1 << tt) : 0;
                 tm8[lane] = m;
@@ -754,20 +859,43 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             for (int j = 0; j < kInRows; ++j) {
                 const long long src = g0 - 3 + j;
                 const bool ok = src >= 0 && src < p.total_rows;
+                uint32_t mb = 0;   // largest |x| of the row as a bit pattern (NaN orders above infinity)
                 for (int b = lane; b < kBins; b += 32) {
                     const float x = ok ? __ldg(p.in + src * kBins + b) : 0.f;
-                    in_amax = fmaxf(in_amax, fabsf(x));   // range guard of the first layer's input
+                    mb = max(mb, __float_as_uint(x) & 0x7fffffffu);
                     ib[j * kInStride + b] = x;
                 }
+                mb = __reduce_max_sync(0xffffffffu, mb);
+                if (lane == 0) s_rmax[j] = mb;
+            }
+            __syncwarp();
+            // The frame's scale: a power of two that puts max(|input rows the frame reads|, largest |bias|) into
+            // [2^(kFrameTop-1), 2^kFrameTop).  Frames without input and a bias-free model: 1.
+            if (lane < 8) {
+                uint32_t fm = 0;
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt)
+                    if ((m >> tt) & 1) fm = max(fm, s_rmax[lane + tt]);
+                float sc = 1.f;
+                if (fm >= 0x7f800000u) {
+                    bad_input = true;   // infinity or NaN: the FP32 kernel recomputes the call
+                } else {
+                    const uint32_t ref = max(fm, bref);
+                    if (ref != 0u) {
+                        int k = 127 + kFrameTop - 1 - (int)(ref >> 23);
+                        if (k < -100) { k = -100; bad_input = true; }   // beyond 2^103: out of any sensible range
+                        if (k > 100) k = 100;
+                        sc = __uint_as_float((uint32_t)(127 + k) << 23);
+                    }
+                }
+                s_scale[(itn & (kScaleRing - 1)) * 8 + lane] = sc;
             }
             __syncwarp();
             // a counter, not an mbarrier: this warp may be two batches ahead of the epilogue warps,
             // which a phase parity could not tell apart
             if (lane == 0) st_release(bars + 8 * kNextInSlot, itn + 1);
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) in_amax = fmaxf(in_amax, __shfl_xor_sync(0xffffffffu, in_amax, d));
-        if (lane == 0) atomicMax(p.flags, __float_as_uint(in_amax));
+        if (bad_input) atomicMax(p.flags, 0x7f800000u);
     } else if (warp == 2) {
         // ================= dependency scout =================
         // Waits, in the MMA thread's issue order, on the mbarriers every (step, tile) depends on and
@@ -813,12 +941,13 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         c.quad = warp & 3;
         c.grp = (warp - kCtrlWarps) >> 2;   // four consecutive warps cover the four lane quadrants
         c.et = (warp - kCtrlWarps) * 32 + lane;
-        c.skip = p.skip + (size_t)blockIdx.x * skip_floats_per_cta(ARCH);
+        c.skip = p.skip + (size_t)s_slot * skip_floats_per_cta(ARCH);
         c.outp = reinterpret_cast<float*>(smem + smem_out_off(ARCH));
         c.pol_last = l2_policy_evict_last();
         c.pol_first = l2_policy_evict_first();
-        float amax = 0.f;
+        uint32_t amax2 = 0u;   // packed FP16 pair: largest |activation| stored
         const float bias_f = s_bias[(NL - 1) * 32];
+        const float c1_f = s_bias[NS * 32 + NL - 1];   // inverse weight scale of the output layer
         // Stages the first layer's input of batch sb (local index sit): "channel" = time tap, rows g-3 .. g+4
         // of the utterance, from the block the prefetch warp has loaded.  Plane 0 must be free.
         auto stage_input = [&](const long long sb, const uint32_t sit) {
@@ -829,19 +958,21 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
             const int* tm8 = reinterpret_cast<const int*>(bnd) + (sit & 1) * 8;
             const float* ib = reinterpret_cast<const float*>(smem + smem_in_off(ARCH)) + (sit & 1) * kInRows * kInStride;
+            const float* fsc = s_scale + (sit & (kScaleRing - 1)) * 8;
 #pragma unroll 1
             for (int r = c.et; r < kRows; r += 32 * kEpiWarps) {
                 const int fi = r / kFS, b = r - fi * kFS;
                 float v[8];
                 if (fi < snf && b < kBins) {
                     const int m = tm8[fi];
+                    const float sfi = fsc[fi];   // into the frame's scaled domain (a power of two: exact)
 #pragma unroll
-                    for (int tt = 0; tt < 8; ++tt) v[tt] = (m >> tt) & 1 ? ib[(fi + tt) * kInStride + b] : 0.f;   // input row fi + tt of the block
+                    for (int tt = 0; tt < 8; ++tt) v[tt] = (m >> tt) & 1 ? ib[(fi + tt) * kInStride + b] * sfi : 0.f;   // input row fi + tt of the block
                 } else {
 #pragma unroll
                     for (int tt = 0; tt < 8; ++tt) v[tt] = 0.f;
                 }
-                store_split8(act, 0, kLead + r, v, true);
+                store_split8(act, 0, kLead + r, v, true, amax2);
             }
             fence_async_smem();
             __syncwarp();
@@ -854,13 +985,14 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             const long long left = p.total_rows - g0;
             c.nf = left < kFB ? (int)left : kFB;
             c.g0 = g0;
+            c.scale = s_scale + (it & (kScaleRing - 1)) * 8;
             c.tracing = p.trace != nullptr && blockIdx.x == 0 && it == 1;
             const uint32_t k0 = it * NS;
 #pragma unroll 1
             for (int s = 0; s < NL - 1; ++s) {
                 const uint32_t par = (k0 + s) & 1;
 #pragma unroll 1
-                for (int t = c.grp; t < kTiles; t += kGroups) epi_conv_tile(c, s, t, par, amax);
+                for (int t = c.grp; t < kTiles; t += kGroups) epi_conv_tile(c, s, t, par, amax2);
             }
             // Output layer.  Between this warp's two row tiles the next batch's input is staged: plane 0 is
             // free as soon as the output layer's MMAs have completed, so the first layer of the next
@@ -880,34 +1012,45 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             for (int i = c.et; i < c.nf * kBins; i += 32 * kEpiWarps) {
                 const int fi = i / kBins, b = i - fi * kBins;
                 const int row = fi * kFS + b;
-                st_hint1(p.out + (g0 + fi) * kBins + b, (c.outp[row] + c.outp[kRows + row]) + bias_f, c.pol_first);
+                // back from the frame's scaled domain: 1 / s of a power of two by exponent arithmetic
+                const float inv = c1_f * __uint_as_float(0x7f000000u - __float_as_uint(c.scale[fi]));
+                st_hint1(p.out + (g0 + fi) * kBins + b, fmaf(c.outp[row] + c.outp[kRows + row], inv, bias_f), c.pol_first);
             }
         }
-        // range guard: non-negative floats order like their bit patterns
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
-        if (lane == 0) atomicMax(p.flags, __float_as_uint(amax));
+        // range guard: non-negative floats order like their bit patterns (an FP16 overflow is an infinity)
+        const float2 am = __half22float2(*reinterpret_cast<const __half2*>(&amax2));
+        uint32_t amax = max(__float_as_uint(am.x), __float_as_uint(am.y));
+        amax = __reduce_max_sync(0xffffffffu, amax);
+        if (lane == 0) atomicMax(p.flags, amax);
     }
 
     fence_before();
     __syncthreads();
+    if (threadIdx.x == 32 && s_slot_owned) scratch_slot_release(p.slot_busy, s_slot);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
 // host side: weight image, launch
 // ------------------------------------------------------------------------------------------
-static inline void split_half(float w, uint16_t& hi, uint16_t& lo) {
+// w = hi + lo as FP16 numbers; lo_scaled = 2^11 lo and hi_down = 2^-11 hi are the forms that meet the
+// scaled residual of the activations (rced_tc.cuh, "Range")
+static inline void split_half(float w, uint16_t& hi, uint16_t& lo, uint16_t& lo_scaled, uint16_t& hi_down) {
     const __half h = __float2half_rn(w);
-    const __half l = __float2half_rn(w - __half2float(h));
+    const float r = w - __half2float(h);
+    const __half l = __float2half_rn(r);
+    const __half ls = __float2half_rn(ldexpf(r, kLoShift));
+    const __half hd = __float2half_rn(ldexpf(__half2float(h), -kLoShift));
     memcpy(&hi, &h, 2);
     memcpy(&lo, &l, 2);
+    memcpy(&lo_scaled, &ls, 2);
+    memcpy(&hi_down, &hd, 2);
 }
 
 }  // namespace tc
 
 int tc_image_bytes(int arch) { return tc::w_image_bytes(arch); }
-int tc_bias_floats(int arch) { return tc::n_steps(arch) * 32; }
+int tc_bias_floats(int arch) { return tc::bias_floats(arch); }
 size_t tc_skip_floats_per_cta(int arch) { return tc::skip_floats_per_cta(arch); }
 int tc_smem_bytes(int arch) { return tc::smem_total(arch); }
 
@@ -916,7 +1059,31 @@ void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* b
     using namespace tc;
     const int nl = num_layers(arch), ns = n_steps(arch);
     memset(img, 0, (size_t)w_image_bytes(arch));
-    for (int i = 0; i < ns * 32; ++i) bias[i] = 0.f;
+    for (int i = 0; i < bias_floats(arch); ++i) bias[i] = 0.f;
+    float bias_ref = 0.f;
+    // Power-of-two weight scales (rced_tc.cuh, "Range").  kw[s]: exponent the weights of step s are scaled by;
+    // dom[s]: exponent of the domain the step's OUTPUT lives in (on top of the frame's scale) = sum of kw up to s.
+    // Conv steps keep kw = 0 while their largest weight lies in [2^-7, 2^3) -- their FP16 image is then as precise as
+    // it gets and the epilogue needs no multiplication; layers outside (BN folds with extreme gamma / variance) are
+    // brought to [2^-2, 2^-1) and the domain of everything behind them shifts with them.  The output layer is always
+    // scaled to [2^12, 2^13): its 2^-11 copy of Whi must stay a normal FP16 number.
+    int kw[kMaxLayers] = {}, dom[kMaxLayers] = {};
+    for (int s = 0; s < ns; ++s) {
+        const int li = step_layer(arch, s);
+        const LSpec sp = spec(arch, li);
+        const float* k = folded + folded_off(arch, li);
+        float wmax = 0.f;
+        for (size_t i = 0; i < (size_t)sp.kh * sp.kw * sp.cin * sp.cout; ++i) wmax = fmaxf(wmax, fabsf(k[i]));
+        int ex = 0;
+        if (wmax > 0.f) frexpf(wmax, &ex);   // wmax = m 2^ex, m in [0.5, 1)
+        if (wmax > 0.f) {
+            if (is_final(arch, s)) kw[s] = kStepWeightTop - ex;
+            else if (ex < -6 || ex > 3) kw[s] = -1 - ex;
+        }
+        if (kw[s] > 100) kw[s] = 100;
+        if (kw[s] < -100) kw[s] = -100;
+        dom[s] = (s > 0 ? dom[s - 1] : 0) + kw[s];
+    }
     uint16_t* im = reinterpret_cast<uint16_t*>(img);
     for (int s = 0; s < ns; ++s) {
         const int li = step_layer(arch, s);
@@ -925,6 +1092,17 @@ void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* b
         const float* b = k + (size_t)sp.kh * sp.kw * sp.cin * sp.cout;
         const int rows = step_tile_rows(arch, s), np = step_np(arch, s), nc = step_chunks(arch, s);
         uint16_t* base = im + step_w_off(arch, s) / 2;
+        const int kwe = kw[s];
+        if (is_final(arch, s)) {
+            bias[ns * 32 + s] = ldexpf(1.f, -dom[s]);   // accumulator -> true output, before the division by the frame's scale
+        } else {
+            // the skip tensor a step adds was saved in the domain of the step that produced it
+            float r = 1.f;
+            if (sp.add >= 0)
+                for (int j = 0; j < s; ++j)
+                    if (spec(arch, j).save == sp.add) r = ldexpf(1.f, dom[s] - dom[j]);
+            bias[ns * 32 + s] = r;
+        }
         for (int u = 0; u < step_units(arch, s); ++u)
             for (int cc = 0; cc < 2; ++cc) {
                 const int ch = is_final(arch, s) ? cc : 2 * u + cc;
@@ -932,8 +1110,8 @@ void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* b
                 for (int n = 0; n < rows; ++n)
                     for (int e = 0; e < 8; ++e) {
                         float w = 0.f;
-                        const bool want_lo = n >= np;
-                        const int nn = want_lo ? n - np : n;
+                        const int blk = n / np;   // 0: Whi, 1: residual (conv steps: times 2^11), 2 (output layer): Whi 2^-11
+                        const int nn = n - blk * np;
                         if (is_final(arch, s)) {
                             // unit u = block of 32 taps: tap j = 32 u + nn, chunk = channel group
                             const int tap = u * kFinalN + nn, ci = 8 * cc + e;
@@ -946,34 +1124,64 @@ void tc_pack_weights(int arch, const float* folded, unsigned char* img, float* b
                                            : k[(((size_t)0 * sp.kw + j) * sp.cin + ci) * sp.cout + nn];
                             }
                         }
-                        uint16_t hi, lo;
-                        split_half(w, hi, lo);
-                        base[((size_t)u * 2 * rows + (size_t)cc * rows + n) * 8 + e] = want_lo ? lo : hi;
+                        uint16_t hi, lo, lo_scaled, hi_down;
+                        split_half(ldexpf(w, kwe), hi, lo, lo_scaled, hi_down);
+                        base[((size_t)u * 2 * rows + (size_t)cc * rows + n) * 8 + e] =
+                            blk == 0 ? hi : (blk == 2 ? hi_down : (is_final(arch, s) ? lo : lo_scaled));
                     }
             }
+        // biases enter the domain of their step; the output layer's bias is added outside the scaled domain
         if (is_final(arch, s)) bias[s * 32] = b[0];
         else
-            for (int o = 0; o < sp.cout; ++o) bias[s * 32 + o] = b[o];
+            for (int o = 0; o < sp.cout; ++o) {
+                bias[s * 32 + o] = ldexpf(b[o], dom[s]);
+                bias_ref = fmaxf(bias_ref, fabsf(bias[s * 32 + o]));
+            }
     }
+    bias[ns * 32 + kBiasRefSlot] = bias_ref;
 }
 
 template <int ARCH>
-static cudaError_t launch_tc_t(const tc::TcParams& p, int num_sms, cudaStream_t stream) {
+static cudaError_t launch_tc_t(const tc::TcParams& p, int num_sms, size_t persist_bytes, cudaStream_t stream) {
     constexpr int smem = tc::smem_total(ARCH);
     static_assert(smem <= 227 * 1024, "activation planes + weight double buffer must fit one SM's shared memory");
-    cudaError_t e = cudaFuncSetAttribute(tc::rced_net_tc_kernel<ARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
+    static bool attr_set[64] = {};   // per instantiation and device; the attribute is sticky
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(tc::rced_net_tc_kernel<ARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     long long ctas = (p.total_rows + tc::kFB - 1) / tc::kFB;
     if (ctas > num_sms) ctas = num_sms;
     if (ctas < 1) return cudaSuccess;
-    tc::rced_net_tc_kernel<ARCH><<<(unsigned)ctas, tc::kThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (persist_bytes > 0) {
+        // the skip scratch is re-written by every batch and read back a few layers later: keep it in the
+        // part of the L2 set aside for persisting lines (cudaLimitPersistingL2CacheSize, set by the caller)
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = p.skip;
+        attr[0].val.accessPolicyWindow.num_bytes = persist_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, tc::rced_net_tc_kernel<ARCH>, p);
 }
 
 int tc_trace_slots(int arch) { return tc::n_steps(arch) * tc::kTiles * tc::kTraceEvents; }
 
 cudaError_t launch_net_tc(int arch, const NetParams& np, const unsigned char* wimg, const float* bias, float* skip,
-                          unsigned int* flags, long long* trace, int num_sms, cudaStream_t stream) {
+                          unsigned int* slot_busy, int n_slots, size_t persist_bytes, unsigned int* flags, long long* trace,
+                          int num_sms, cudaStream_t stream) {
     tc::TcParams p;
     p.wimg = wimg;
     p.bias = bias;
@@ -983,12 +1191,14 @@ cudaError_t launch_net_tc(int arch, const NetParams& np, const unsigned char* wi
     p.n_utt = np.n_utt;
     p.total_rows = np.total_rows;
     p.skip = skip;
+    p.slot_busy = slot_busy;
+    p.n_slots = n_slots;
     p.flags = flags;
     p.trace = trace;
     switch (arch) {
-        case 1: return launch_tc_t<1>(p, num_sms, stream);
-        case 2: return launch_tc_t<2>(p, num_sms, stream);
-        case 3: return launch_tc_t<3>(p, num_sms, stream);
+        case 1: return launch_tc_t<1>(p, num_sms, persist_bytes, stream);
+        case 2: return launch_tc_t<2>(p, num_sms, persist_bytes, stream);
+        case 3: return launch_tc_t<3>(p, num_sms, persist_bytes, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -11,6 +11,25 @@
 //   x*w ~= hi*Whi + hi*Wlo + lo*Whi     (FP32 accumulation in tensor memory)
 // issued as two instructions per K step: A_hi x [Whi | Wlo] (N = 2*NP) and A_lo x Whi (N = NP).
 //
+// Range (the FP16 exponent has 5 bits).  Three power-of-two scalings, all exact in FP32, keep every
+// FP16 operand in its normal range whatever the scale of the input or of the weights:
+//  * the residuals are stored times 2^11 (lo' = 2^11 (x - hi), Wlo' = 2^11 (w - Whi)), so they have the
+//    magnitude of the value itself instead of falling into the FP16 subnormals; the two cross products
+//    hi*Wlo' + lo'*Whi accumulate in their own columns [NP, 2 NP) and the epilogue adds them times 2^-11;
+//  * a step's weights are scaled by 2^kw when its largest weight lies outside [2^-7, 2^3) (conv steps: to
+//    [2^-2, 2^-1); BN folds with extreme gamma or variance) and always for the output layer (to
+//    [2^12, 2^13), kStepWeightTop); the domain of every later activation shifts by 2^kw with it -- the
+//    host pre-scales the biases, the skip additions multiply by the power of two between the two
+//    domains (table behind the biases), and the output is multiplied by the inverse of the total;
+//  * every FRAME of a batch is computed in its own scaled domain x' = s x, s = 2^k chosen by the prefetch
+//    warp so that max(|input of the frame|, largest |bias|) s lies in [2^3, 2^4) (kFrameTop): rows of
+//    different frames never meet in a conv layer (the time taps of the first layer are the channels of
+//    the frame's own rows), ReLU and the skip additions commute with s, biases are added times s and
+//    the output is multiplied by 1/s.
+// An activation keeps its 22 bits while it lies within [2^-14, 65504] of the scaled domain, i.e. between
+// 4e-6 and 4000 times the frame's reference magnitude; beyond 65504 the range guard hands the call to
+// the FP32 FFMA kernel.
+//
 // The (1,129) output layer runs "taps in N with row-shifted accumulation": tap j = 32 i + n
 // (i = 0..4, n = 0..31), E[r][n] = sum_i X[r + 32 (i - 2)] . W[32 i + n] -- five MMAs whose A
 // descriptors are shifted by 32 (i - 2) rows accumulate into the same 32 columns -- and
@@ -51,6 +70,10 @@ constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
 constexpr int kTraceEvents = 8;               // clock stamps per (step, tile) of the development trace
 constexpr int kInRows = kFB + 7;              // input rows a batch reads: frames g0-3 .. g0+kFB+3
 constexpr int kInStride = 132;                // floats per prefetched input row
+constexpr int kLoShift = 11;                  // residuals (activations and weights) are stored times 2^kLoShift
+constexpr int kStepWeightTop = 13;            // the output layer's weights are scaled so that max |w| lies in [2^12, 2^13)
+constexpr int kFrameTop = 4;                  // a frame's scale puts max(|input|, |bias|) into [2^3, 2^4)
+constexpr int kScaleRing = 4;                 // batches whose frame scales are kept (the epilogue of a batch reads them until it ends)
 
 static_assert(kFB * kFS <= kRows, "frames of a batch must fit the row tiles");
 static_assert(kFS - kBins >= 6 && kLead >= 6, "zero rows must cover the widest SAME pad (kw = 13)");
@@ -71,8 +94,10 @@ RCED_HD constexpr int step_chunks(int arch, int s) {
 // units: pairs of (tap, group) chunks of a conv layer; the row-shifted blocks of the output layer (whose
 // two chunks are the channel groups, at most 16 channels)
 RCED_HD constexpr int step_units(int arch, int s) { return is_final(arch, s) ? kFinalShifts : (step_chunks(arch, s) + 1) / 2; }
-// B tile of one unit: [2 chunks][rows][8 halfs]; rows = 2*NP (Whi | Wlo)
-RCED_HD constexpr int step_tile_rows(int arch, int s) { return 2 * step_np(arch, s); }
+// B tile of one unit: [2 chunks][rows][8 halfs]; conv steps: rows = 2*NP (Whi | Wlo'), output layer: 3*NP
+// (Whi | Wlo | Whi 2^-11: its three products share one accumulator block, so the scaled residual of the
+// activations meets a copy of the weights that carries the 2^-11)
+RCED_HD constexpr int step_tile_rows(int arch, int s) { return (is_final(arch, s) ? 3 : 2) * step_np(arch, s); }
 RCED_HD constexpr int step_tile_bytes(int arch, int s) { return 2 * step_tile_rows(arch, s) * 16; }
 RCED_HD constexpr int step_w_bytes(int arch, int s) { return step_units(arch, s) * step_tile_bytes(arch, s); }
 RCED_HD constexpr int step_w_off(int arch, int s) {
@@ -144,9 +169,16 @@ RCED_HD constexpr size_t skip_floats_per_cta(int arch) { return (size_t)skip_c8_
 RCED_HD constexpr int pad128(int x) { return (x + 127) & ~127; }
 constexpr int smem_act_off = kFrontPad;   // activation planes, behind the zero rows
 RCED_HD constexpr int smem_w_off(int arch, int buf) { return kFrontPad + kActBytes + buf * pad128(max_step_w_bytes(arch)); }
-RCED_HD constexpr int smem_bias_off(int arch) { return smem_w_off(arch, 2); }                                   // float[n_steps][32]
-RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 128 * n_steps(arch); }             // float[2][kRows]: the two partial sums of every output row
-RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + 2 * kRows * 4; }                    // long long[2][kFB][2]
+// bias table (global and shared): float[n_steps + 1][32]; row s: biases of step s, in the step's domain; row
+// n_steps: [s] = conv step s: power of two between the domain of the skip tensor it adds and its own, output
+// layer: inverse of the total weight scale; [kBiasRefSlot] = largest |bias| of the model (in its domain)
+constexpr int kBiasRefSlot = 16;
+RCED_HD constexpr int bias_floats(int arch) { return 32 * (n_steps(arch) + 1); }
+RCED_HD constexpr int smem_bias_off(int arch) { return smem_w_off(arch, 2); }                                   // float[n_steps + 1][32]
+RCED_HD constexpr int smem_out_off(int arch) { return smem_bias_off(arch) + 4 * bias_floats(arch); }           // float[2][kRows]: the two partial sums of every output row
+// 256 bytes: int[2][8] time-tap masks of the prefetched batches, float[kScaleRing][8] frame scales (+64),
+// float[16] row maxima of the batch being prefetched (+192)
+RCED_HD constexpr int smem_bnd_off(int arch) { return smem_out_off(arch) + 2 * kRows * 4; }
 RCED_HD constexpr int smem_bar_off(int arch) { return smem_bnd_off(arch) + 256; }                              // mbarriers
 RCED_HD constexpr int smem_epi_off(int arch) { return smem_bar_off(arch) + 256; }                             // EpiStep[n_steps]
 RCED_HD constexpr int smem_in_off(int arch) { return smem_epi_off(arch) + pad128(32 * n_steps(arch)); }       // float[2][kInRows][kInStride]

@@ -62,8 +62,8 @@ class Enhancer(object):
         (model_utils/utils.py:94), 256 is the mathematically consistent inverse.
         ``variant``: network kernel, "tc" (tcgen05 tensor cores with the FP16 x3 split, the FP32 FFMA
         kernel behind it as range-guard fall-back; default) or "ffma" (FP32 FFMA kernel only).  "tc" is
-        refused by the library when a folded weight exceeds the FP16 range; the engine then stays on
-        "ffma" (``self.variant`` tells which kernel runs)."""
+        refused by the library (RCED_ERR_STATE) when a folded weight is not finite; the engine then stays
+        on "ffma" (``self.variant`` tells which kernel runs).  Any other failure (CUDA errors) is raised."""
         if not torch.cuda.is_available():
             raise _lib.RcedError("no CUDA device: the enhancement path has no CPU fallback")
         self.lib = _lib.lib()
@@ -87,8 +87,9 @@ class Enhancer(object):
         if variant == "tc":
             try:
                 self.set_variant("tc")
-            except _lib.RcedError:
-                pass
+            except _lib.RcedError as exc:
+                if exc.code != _lib.ERR_STATE:
+                    raise
         elif variant != "ffma":
             raise ValueError("variant must be 'tc' or 'ffma'")
 

@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
     unsigned char* dimg;
     float *dbias, *dx, *dy, *dskip;
     long long *dro, *dtrace = nullptr;
-    unsigned int* dflags;
+    unsigned int *dflags, *dbusy;
     cudaMalloc(&dimg, img.size());
     cudaMalloc(&dbias, bias.size() * 4);
     cudaMalloc(&dx, x.size() * 4);
@@ -55,6 +55,19 @@ int main(int argc, char** argv) {
     cudaMalloc(&dskip, (size_t)nsm * tc_skip_floats_per_cta(arch) * 4);
     cudaMalloc(&dflags, 8);
     cudaMemset(dflags, 0, 8);
+    cudaMalloc(&dbusy, nsm * 4);
+    cudaMemset(dbusy, 0, nsm * 4);
+    // L2 persistence experiment: K2TC_PERSIST=1 sets aside persisting L2 and passes an access-policy window
+    size_t persist = 0;
+    if (getenv("K2TC_PERSIST") && atoi(getenv("K2TC_PERSIST")) > 0) {
+        size_t want = (size_t)nsm * tc_skip_floats_per_cta(arch) * 4;
+        persist = want;
+        if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        if (persist > (size_t)prop.accessPolicyMaxWindowSize) persist = (size_t)prop.accessPolicyMaxWindowSize;
+        printf("persisting L2 max %d MB, window max %d MB, L2 %d MB -> limit %zu MB, window %zu MB\n", prop.persistingL2CacheMaxSize >> 20,
+               prop.accessPolicyMaxWindowSize >> 20, prop.l2CacheSize >> 20, want >> 20, persist >> 20);
+    }
     cudaMemcpy(dimg, img.data(), img.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(dbias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
@@ -72,7 +85,8 @@ int main(int argc, char** argv) {
     float best = 1e30f;
     for (int r = 0; r < 5; ++r) {
         cudaEventRecord(a);
-        cudaError_t e = launch_net_tc(arch, p, dimg, dbias, dskip, dflags, r == 4 ? dtrace : nullptr, nsm, 0);
+        cudaMemsetAsync(dflags, 0, 8, 0);
+        cudaError_t e = launch_net_tc(arch, p, dimg, dbias, dskip, dbusy, nsm, persist, dflags, r == 4 ? dtrace : nullptr, nsm, 0);
         cudaEventRecord(b);
         cudaEventSynchronize(b);
         if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 1; }

@@ -14,8 +14,12 @@ VARIANTS=(
   "l2hint:-DRCED_TC_SKIPHINT=1"
   "l1bypass:-DRCED_TC_SKIPHINT=3"
   "validrows:-DRCED_TC_DIAG_VALIDROWS"
+  "saveinline:-DRCED_TC_SAVE_INLINE"
   "noskip_DIAG:-DRCED_TC_DIAG_NOSKIP"
+  "nosave_DIAG:-DRCED_TC_DIAG_NOSAVE"
+  "noadd_DIAG:-DRCED_TC_DIAG_NOADD"
 )
+# RCED_K2TC_ONLY="default saveinline" restricts the run to some variants
 case "$1" in
   build)
     ./build_k2tc_variants.sh "${VARIANTS[@]}"
@@ -26,10 +30,12 @@ case "$1" in
     : > "$out"
     for v in "${VARIANTS[@]}"; do
       name="${v%%:*}"
-      for arch in 2 1 3; do
+      if [ -n "$RCED_K2TC_ONLY" ] && ! echo " $RCED_K2TC_ONLY " | grep -q " $name "; then continue; fi
+      for arch in ${RCED_K2TC_ARCHS:-2 1 3}; do
         timeout 60 ./k2v/"$name" $arch "$name" | tee -a "$out"
       done
     done
+    K2TC_PERSIST=1 timeout 60 ./k2v/default 2 persist | tee -a "$out"
     timeout 60 ./k2v/default 2 trace ../gpurun_out/tc_trace.txt > /dev/null && python tc_trace_report.py ../gpurun_out/tc_trace.txt | grep -E "first_poll|total" >> "$out"
     ;;
   *)

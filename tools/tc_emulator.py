@@ -4,7 +4,9 @@ It executes exactly the address arithmetic of csrc/rced_net_tc.cu on the CPU: th
 weight image and bias table produced by rced_tc_pack_weights, the per-unit A-descriptor table of
 rced_tc_layout (start offset and leading-dimension offset in 16-byte units, rows linear at 16
 bytes), the flattened (frame, bin) row space with its zero halo rows, in-place plane updates,
-the two instructions per K step (A_hi x [Whi | Wlo], A_lo x Whi) with FP32 accumulation, the
+the two instructions per K step (A_hi x [Whi | Wlo'] into columns [0, 2 NP), A_lo' x Whi into columns
+[NP, 2 NP), residuals stored times 2^11) with FP32 accumulation, the power-of-two scalings (per step weight
+scale, per frame activation scale chosen from the frame's input rows and the largest bias), the
 even / odd frame copies written by the last conv layer, the row-shifted blocks of the (1,129) layer
 (reads before plane 0 land in the zero front rows) with its 32-column diagonal sums, and the FP32
 skip scratch.
@@ -44,11 +46,27 @@ def pack(lib, arch, folded):
     return img, bias
 
 
+LO_SHIFT = 11        # residuals are stored times 2^11 (csrc/rced_tc.cuh: kLoShift)
+FRAME_TOP = 4        # a frame's reference magnitude lands in [2^3, 2^4) (kFrameTop)
+BIAS_REF_SLOT = 16   # kBiasRefSlot
+
+
 def split(v):
     v = np.asarray(v, np.float32)
     hi = v.astype(np.float16)
-    lo = (v - hi.astype(np.float32)).astype(np.float16)
+    lo = ((v - hi.astype(np.float32)) * np.float32(2.0 ** LO_SHIFT)).astype(np.float16)
     return hi, lo
+
+
+def frame_scale(ref):
+    """Power of two that puts `ref` (float32, finite, >= 0) into [2^(FRAME_TOP-1), 2^FRAME_TOP): exponent arithmetic on the
+    bit pattern, like the prefetch warp."""
+    bits = int(np.float32(ref).view(np.uint32))
+    if bits == 0:
+        return np.float32(1.0)
+    k = 127 + FRAME_TOP - 1 - (bits >> 23)
+    k = max(-100, min(100, k))
+    return np.float32(2.0 ** k)
 
 
 def run(lib, arch, folded, mag, row_off, table):
@@ -65,8 +83,14 @@ def run(lib, arch, folded, mag, row_off, table):
     total = mag.shape[0]
     pred = np.zeros((total, BINS), np.float32)
     nl = len(table)
+    ns = lay["ns"]
     scopes = [L["scope"] for L in table]
     amax = 0.0
+    # per conv step: power of two between the domain of the skip tensor it adds and its own; output layer: inverse of
+    # the total weight scale (the biases of the table are already in their step's domain)
+    aux = bias[ns * 32: ns * 32 + ns].astype(np.float32)
+    bias_ref = np.float32(bias[ns * 32 + BIAS_REF_SLOT])
+    lo_inv = np.float32(2.0 ** -LO_SHIFT)
 
     r_idx = np.arange(ROWS)
     fi_of, b_of = r_idx // FS, r_idx % FS
@@ -81,14 +105,22 @@ def run(lib, arch, folded, mag, row_off, table):
         flat[FR + 2 * LO16:] = 3.0
         # ---- staging of the first layer's input ("channel" = time tap)
         v = np.zeros((ROWS, 8), np.float32)
+        fscale = np.ones(8, np.float32)          # per frame: power-of-two scale of its domain
         for fi in range(nf):
             g = g0 + fi
             u = int(np.searchsorted(row_off, g, side="right") - 1)
             lo_, hi_ = row_off[u], row_off[u + 1]
+            fmax = np.float32(0)
             for tt in range(8):
                 src = g + tt - 3
                 if lo_ <= src < hi_:
                     v[fi * FS: fi * FS + BINS, tt] = mag[src]
+                    fmax = max(fmax, np.abs(mag[src]).max())
+            fscale[fi] = frame_scale(max(fmax, bias_ref))
+            v[fi * FS: fi * FS + BINS] *= fscale[fi]
+        for fi in range(nf, 8):
+            fscale[fi] = frame_scale(bias_ref)
+        rscale = fscale[np.minimum(fi_of, 7)]    # per row
         amax = max(amax, float(np.abs(v).max()))
         h, l = split(v)
         flat[FR + LEAD: FR + LEAD + ROWS] = h
@@ -97,7 +129,7 @@ def run(lib, arch, folded, mag, row_off, table):
         outp = np.full((2, ROWS), np.nan, np.float32)
         for s, st in enumerate(lay["steps"]):
             NP = st["np"]
-            rows_b = 2 * NP
+            rows_b = (3 if st["final"] else 2) * NP
             tile_h = st["tile_bytes"] // 2
             D = np.zeros((ROWS, 64), np.float32)
             for t in range(TILES):
@@ -120,7 +152,7 @@ def run(lib, arch, folded, mag, row_off, table):
                                 D[sl, :rows_b] = pa
                             else:
                                 D[sl, :rows_b] += pa
-                            D[sl, :NP] += a_lo @ B[:NP].T
+                            D[sl, NP:2 * NP] += a_lo @ B[:NP].T      # both cross products carry 2^11
                         else:
                             c0 = odd * NP
                             pa = a_hi @ B[:NP].T
@@ -128,22 +160,23 @@ def run(lib, arch, folded, mag, row_off, table):
                                 D[sl, c0:c0 + NP] = pa
                             else:
                                 D[sl, c0:c0 + NP] += pa
-                            D[sl, c0:c0 + NP] += a_lo @ B[:NP].T
-                            D[sl, c0:c0 + NP] += a_hi @ B[NP:].T
+                            D[sl, c0:c0 + NP] += a_lo @ B[2 * NP:].T      # scaled residual x (Whi 2^-11)
+                            D[sl, c0:c0 + NP] += a_hi @ B[NP:2 * NP].T    # hi x Wlo (not scaled)
             if not st["final"]:
                 L = table[s]
                 cout = L["cout"]
                 cg = (cout + 7) // 8
-                x = D[:, :cg * 8] + D[:, NP:NP + cg * 8] + bias[s * 32: s * 32 + cg * 8]
+                x = (D[:, :cg * 8] + D[:, NP:NP + cg * 8] * lo_inv).astype(np.float32)
+                x = (x + bias[s * 32: s * 32 + cg * 8][None, :] * rscale[:, None]).astype(np.float32)
                 if L["skip"] is not None and not L["skip_after_act"]:
-                    x = x + saved[L["skip"]]
+                    x = (x + saved[L["skip"]] * aux[s]).astype(np.float32)
                 if L["act"]:
                     x = np.maximum(x, 0)
                 if L["skip"] is not None and L["skip_after_act"]:
-                    x = x + saved[L["skip"]]
+                    x = (x + saved[L["skip"]] * aux[s]).astype(np.float32)
                 x = np.where(valid[:, None], x, 0).astype(np.float32)
                 amax = max(amax, float(np.abs(x).max()))
-                saved[scopes[s]] = x
+                saved[scopes[s]] = x[:, :cg * 8]
                 h, l = split(x)
                 last = s == nl - 2
                 odd_row = (fi_of % 2 == 1)[:, None]
@@ -185,5 +218,6 @@ def run(lib, arch, folded, mag, row_off, table):
                                     outp[1, rb] = prev[m]
         bias_f = bias[(nl - 1) * 32]
         for fi in range(nf):
-            pred[g0 + fi] = (outp[0, fi * FS: fi * FS + BINS] + outp[1, fi * FS: fi * FS + BINS]) + bias_f
+            inv = np.float32(aux[nl - 1]) / fscale[fi]    # a power of two
+            pred[g0 + fi] = (outp[0, fi * FS: fi * FS + BINS] + outp[1, fi * FS: fi * FS + BINS]) * inv + bias_f
     return pred, amax
