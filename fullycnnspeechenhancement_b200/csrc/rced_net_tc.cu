@@ -242,6 +242,21 @@ __device__ __forceinline__ void st_hint1(float* p, const float v, uint64_t pol) 
     *p = v;
 #endif
 }
+// Skip tensors by bulk copy (experiment switch RCED_TC_SKIP_BULK=1, off): a saving layer's rows go from the FP16
+// hi / lo planes to the global scratch with cp.async.bulk issued AFTER the tile has been released -- the async proxy
+// reads the planes, no thread has a global store outstanding when the next proxy fence (MEMBAR.ALL.CTA +
+// FENCE.VIEW.ASYNC) runs.  Measured on B200 (tools/k2tc_experiments.sh, V2, 254,976 frames): 15.30 ms against
+// 13.59 ms for the store form (FP32 rows written from the registers in front of the fence; no skip traffic at
+// all: 13.16 ms) -- 1,088 512-byte copies per batch are slower than the L2 round trip they avoid.
+#ifndef RCED_TC_SKIP_BULK
+#define RCED_TC_SKIP_BULK 0
+#endif
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 
 // K-major, no-swizzle shared-memory matrix descriptor (version 1): start and LBO in the low word,
@@ -450,8 +465,10 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
     const float sf = c.scale[fi];                    // the frame's scale: the (pre-scaled) biases enter its domain times sf
     const u64 sf2 = pack2(sf, sf), loinv2 = pack2(kLoInv, kLoInv), r2 = pack2(e.skip_r, e.skip_r);
     const uint32_t ta = c.tm + ((uint32_t)(c.quad * 32) << 16) + (uint32_t)(t * kAccCols);
-    // Skip tensors: FP32 in a per-CTA global scratch (L2), [group of 8 channels][half][row][4 floats], so
-    // that a warp's 16-byte accesses cover whole sectors.  The row is saved and added by the same thread.
+    // Skip tensors: in the CTA's region of the global scratch (L2), [group of 8 channels][half][row][16 bytes], so
+    // that a warp's 16-byte accesses cover whole sectors.  The row is saved and added by the same warp.  Bulk form:
+    // half 0 = the row's 8 FP16 hi values, half 1 = its 8 scaled residuals (copies of the plane rows); store form:
+    // the two halves are FP32 channels 0-3 and 4-7.
     const float4* sp = reinterpret_cast<const float4*>(c.skip) + ((size_t)e.add_base * 2 * kRows + r);
     float4* dp = reinterpret_cast<float4*>(c.skip) + ((size_t)(e.save_base < 0 ? 0 : e.save_base) * 2 * kRows + r);
     // the skip row does not depend on the accumulator: the L2 latency of its first group hides behind
@@ -462,10 +479,21 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
     const bool do_add = e.add != 0, do_save = e.save_base >= 0;
 #endif
     float4 sk0 = make_float4(0.f, 0.f, 0.f, 0.f), sk1 = sk0;
+#if RCED_TC_SKIP_BULK
+    if (do_add) {
+        // the copies that saved the tensor have completed and their writes are visible to this warp (nothing is
+        // pending after the first adding layer of a batch); the loads bypass the L1, which the copies do not update
+        if (c.lane == 0) bulk_wait_all();
+        __syncwarp();
+        sk0 = __ldcg(sp);
+        sk1 = __ldcg(sp + kRows);
+    }
+#else
     if (do_add) {
         sk0 = ld_hint4(sp, c.pol_last);
         sk1 = ld_hint4(sp + kRows, c.pol_last);
     }
+#endif
     // The planes are updated in place: this tile's rows are read by its own MMAs and, as halo, by the
     // MMAs of both neighbour tiles.  The tiles are issued by different threads, each committing in its
     // own order, so all three commits are waited for.
@@ -478,6 +506,11 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
 #endif
     fence_after();
     stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 2);
+#if RCED_TC_SKIP_BULK
+    // the bulk copies that read this warp's plane rows (the skip tensor a previous step saved) have finished reading
+    if (c.lane == 0) bulk_wait_read_all();
+    __syncwarp();
+#endif
 
     float d1[8], d2[8];
     tmem_ld8(ta, d1);
@@ -492,7 +525,21 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
         const float4 b0 = *reinterpret_cast<const float4*>(bias + g * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#if RCED_TC_SKIP_BULK
+        float ss[8];   // hi + 2^-11 lo'
+        {
+            const uint32_t hh[4] = {__float_as_uint(sk0.x), __float_as_uint(sk0.y), __float_as_uint(sk0.z), __float_as_uint(sk0.w)};
+            const uint32_t ll[4] = {__float_as_uint(sk1.x), __float_as_uint(sk1.y), __float_as_uint(sk1.z), __float_as_uint(sk1.w)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
+                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&ll[i]));
+                unpack2(fma2(pack2(lf.x, lf.y), loinv2, pack2(hf.x, hf.y)), ss[2 * i], ss[2 * i + 1]);
+            }
+        }
+#else
         const float ss[8] = {sk0.x, sk0.y, sk0.z, sk0.w, sk1.x, sk1.y, sk1.z, sk1.w};
+#endif
         float v[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -518,11 +565,16 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
             tmem_ld8(ta + (g + 1) * 8, d1);
             tmem_ld8(ta + e.np + (g + 1) * 8, d2);
             if (do_add) {
+#if RCED_TC_SKIP_BULK
+                sk0 = __ldcg(sp + (size_t)(g + 1) * 2 * kRows);
+                sk1 = __ldcg(sp + (size_t)(g + 1) * 2 * kRows + kRows);
+#else
                 sk0 = ld_hint4(sp + (size_t)(g + 1) * 2 * kRows, c.pol_last);
                 sk1 = ld_hint4(sp + (size_t)(g + 1) * 2 * kRows + kRows, c.pol_last);
+#endif
             }
         }
-#ifndef RCED_TC_SAVE_DEFERRED   // the skip row is stored from the registers, in front of the fence
+#if !RCED_TC_SKIP_BULK && !defined(RCED_TC_SAVE_DEFERRED)   // the skip row is stored from the registers, in front of the fence
         if (do_save) {
             st_hint4(dp + (size_t)g * 2 * kRows, make_float4(v[0], v[1], v[2], v[3]), c.pol_last);
             st_hint4(dp + (size_t)g * 2 * kRows + kRows, make_float4(v[4], v[5], v[6], v[7]), c.pol_last);
@@ -536,7 +588,20 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
     __syncwarp();
     if (c.lane == 0) mbar_arrive(bar_addr(c, kBarActReady + t));
     stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 4);
-#ifdef RCED_TC_SAVE_DEFERRED
+#if RCED_TC_SKIP_BULK
+    if (do_save && c.lane == 0) {
+        // this warp's 32 rows of every hi and lo plane of the layer: 512 contiguous bytes each
+        const int r0 = t * 128 + c.quad * 32;
+        const uint32_t src = smem_u32(c.act) + (uint32_t)(kLead + r0) * 16u;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(c.skip) + ((size_t)e.save_base * 2 * kRows + r0) * 16;
+#pragma unroll 1
+        for (int g = 0; g < e.cg; ++g) {
+            bulk_s2g(dst + (size_t)g * 2 * kRows * 16, src + (uint32_t)(g * kPlane16) * 16u, 512u);
+            bulk_s2g(dst + ((size_t)g * 2 + 1) * kRows * 16, src + (uint32_t)(g * kPlane16 + kLo16) * 16u, 512u);
+        }
+        bulk_commit();
+    }
+#elif defined(RCED_TC_SAVE_DEFERRED)
     // Experiment (measured slower: 14.46 against 13.92 ms, the extra instructions cost more than the MEMBAR
     // of the proxy fence waiting for the stores): the skip tensor of the tile written AFTER the tile has
     // been released, its values read back from the planes -- this thread's own row, which nobody overwrites
@@ -1017,6 +1082,9 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 st_hint1(p.out + (g0 + fi) * kBins + b, fmaf(c.outp[row] + c.outp[kRows + row], inv, bias_f), c.pol_first);
             }
         }
+#if RCED_TC_SKIP_BULK
+        if (lane == 0) bulk_wait_all();   // no bulk copy may still read this CTA's shared memory when it exits
+#endif
         // range guard: non-negative floats order like their bit patterns (an FP16 overflow is an infinity)
         const float2 am = __half22float2(*reinterpret_cast<const __half2*>(&amax2));
         uint32_t amax = max(__float_as_uint(am.x), __float_as_uint(am.y));

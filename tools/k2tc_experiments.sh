@@ -14,7 +14,8 @@ VARIANTS=(
   "l2hint:-DRCED_TC_SKIPHINT=1"
   "l1bypass:-DRCED_TC_SKIPHINT=3"
   "validrows:-DRCED_TC_DIAG_VALIDROWS"
-  "saveinline:-DRCED_TC_SAVE_INLINE"
+  "skipbulk:-DRCED_TC_SKIP_BULK=1"
+  "skipdeferred:-DRCED_TC_SAVE_DEFERRED"
   "noskip_DIAG:-DRCED_TC_DIAG_NOSKIP"
   "nosave_DIAG:-DRCED_TC_DIAG_NOSAVE"
   "noadd_DIAG:-DRCED_TC_DIAG_NOADD"

@@ -176,7 +176,7 @@ def run(lib, arch, folded, mag, row_off, table):
                     x = (x + saved[L["skip"]] * aux[s]).astype(np.float32)
                 x = np.where(valid[:, None], x, 0).astype(np.float32)
                 amax = max(amax, float(np.abs(x).max()))
-                saved[scopes[s]] = x[:, :cg * 8]
+                saved[scopes[s]] = x[:, :cg * 8]      # FP32 rows, written from the registers
                 h, l = split(x)
                 last = s == nl - 2
                 odd_row = (fi_of % 2 == 1)[:, None]
