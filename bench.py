@@ -26,7 +26,6 @@ sys.path.insert(0, ROOT)
 NET_WORK = "FullyCNNV2"
 N_UTT = 1024                 # BASELINE.json configs[1]
 UTT_SAMPLES = 32000          # 4 s @ 8 kHz
-E2E_CHUNKS = [int(c) for c in os.environ.get("RCED_E2E_CHUNKS", "32,96,128,128,128,128,128,128,96,32").split(",")]   # utterances per chunk of the host pipeline
 SAMPLE_RATE = 8000
 POOL = 64                    # distinct synthetic utterances, tiled to N_UTT
 METRIC = "R-CED V2 audio-seconds enhanced per second"
@@ -137,6 +136,9 @@ class ClockSampler(object):
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+REF_UTTS_PER_STEP = 64     # bounded sample of the 1024-utterance batch the CPU arm enhances per step
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port: TensorFlow
     1.14 cannot be installed) on the box's host cores, rank 0 only."""
@@ -146,9 +148,9 @@ def reference_arm(args, rank, world):
     from oracle import network
     cores = host_cores()
     torch.set_num_threads(cores)
-    pool = synth_pool()[:32]
+    pool = synth_pool()
     weights = network.random_weights(NET_WORK, seed=0, randomize_bn=False)
-    per_step, batch = 32, 32
+    per_step, batch = REF_UTTS_PER_STEP, 32
     for _ in range(args.warmup):
         run_cpu_path(pool, weights, per_step, batch)
     timings = {}
@@ -157,15 +159,17 @@ def reference_arm(args, rank, world):
         run_cpu_path(pool, weights, per_step, batch, timings)
     t = time.perf_counter() - t0
     value = args.steps * per_step * UTT_SAMPLES / SAMPLE_RATE / t
-    sample = ("each step = %d x 4 s utterances (bounded sample of the 1024-utterance batch), batch %d, %d threads, %s; "
-              "stage seconds stft=%.2f network=%.2f rebuild=%.2f" % (per_step, batch, cores, cpu_model(),
-                                                                       timings["stft"], timings["network"], timings["rebuild"]))
+    sample = ("each step = %d x 4 s utterances in batches of %d -- a bounded sample of the 1024-utterance batch of the GPU arm "
+              "(throughput-normalised: audio-seconds per second), %d threads, %s; stage seconds stft=%.2f network=%.2f "
+              "rebuild=%.2f" % (per_step, batch, cores, cpu_model(), timings["stft"], timings["network"], timings["rebuild"]))
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "R-CED V2 (FullyCNNV2) enhancement of 4 s 8 kHz synthetic noisy utterances, CPU",
-                   "utterances_per_step": per_step},
+                   "utterances_per_step": per_step,
+                   "note": "the GPU arm enhances 1024 utterances per step; the CPU arm a bounded sample of %d of the same "
+                           "utterances per step, both reported as audio-seconds enhanced per second" % per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -183,21 +187,34 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)"}
 
 
-def roofline(variant, achieved, ffma_peak, flops_valid, k2_ms, share, traffic, rows, tc_status):
-    """Roofline object of the dominant kernel (the fused network).  `achieved` is algorithmic:
-    valid-tap MACs x 2 per launch / mean launch time measured with CUDA events in the timed steps."""
-    common = {"achieved": achieved, "unit": "TFLOP/s", "flops_per_launch": flops_valid,
-              "flop_basis": "valid-tap MACs x2 (3,959,092 MAC/frame), FP32-equivalent", "kernel_ms": k2_ms,
-              "kernel_share_of_step": share}
-    if variant != "tc":
-        common.update({"bound": "fp32_ffma", "kernel": "rced_net_kernel<2,TMEM> (fused 16-layer network)", "peak": ffma_peak,
-                       "frac": achieved / ffma_peak, "traffic": traffic,
-                       "peak_source": "measured in this run by rced_ffma_peak (independent FFMA chains, 64 warps/SM); "
-                                      "MEASURED_PEAKS.json holds no FP32 figure; nominal 2*128*148*1.965 GHz = 74.4"})
-        return common
-    pk = measured_peaks()
-    # tensor-core work actually issued (DESIGN.md section 4): per 128-row tile and unit (two (tap, 8-channel) chunks,
-    # K = 16) A_hi x [Whi|Wlo] (N = 2 NP) and A_lo x Whi (N = NP); 8 tiles per 7-frame batch; output layer 5 row-shifted blocks
+def source_sha(*names):
+    """sha256 (16 hex digits) of the kernel sources a profile refers to: tells whether a committed ncu figure
+    still describes the kernel that was just timed."""
+    import hashlib
+    h = hashlib.sha256()
+    for n in names:
+        with open(os.path.join(ROOT, "fullycnnspeechenhancement_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_figures(name, sources):
+    """profiles/<name>: what one `ncu --set full` capture of the kernel measured (tools/ncu_digest.py --json writes it),
+    or None.  `kernel_source_matches` says whether the capture was taken from the sources timed now."""
+    path = os.path.join(ROOT, "profiles", name)
+    try:
+        d = json.load(open(path))
+    except (OSError, ValueError):
+        return None
+    d["file"] = "profiles/" + name
+    d["kernel_source_matches"] = d.get("kernel_source_sha16") == source_sha(*sources)
+    return d
+
+
+def tc_issue_model(rows):
+    """Tensor-core work the K2-TC kernel issues from the library's own step table: per 128-row tile
+    and unit (two (tap, 8-channel) chunks, K = 16) A_hi x [Whi|Wlo'] (N = 2 NP) and A_lo' x Whi (N = NP); 8 tiles per
+    7-frame batch; output layer: 5 row-shifted blocks x 3 products for 14 of the 16 (tile, parity) pairs."""
     import ctypes as ct
     from fullycnnspeechenhancement_b200 import _lib
     out = (ct.c_int64 * 4096)()
@@ -206,24 +223,33 @@ def roofline(variant, achieved, ffma_peak, flops_valid, k2_ms, share, traffic, r
     mac_tile, cyc_tile = 0, 0.0
     for st in range(ns):
         units, npad, final = out[16 + 6 * st], out[18 + 6 * st], out[21 + 6 * st]
-        if final:   # row-shifted blocks x 3 products, for the even- and the odd-frame copy (14 of 16 tile-parity pairs)
+        if final:
             mac_tile += 1.75 * units * 3 * 128 * npad * 16
             cyc_tile += 1.75 * units * 3 * (32 + npad / 4.0)
         else:
             mac_tile += units * 128 * 16 * 3 * npad
             cyc_tile += units * ((32 + 2 * npad / 4.0) + (32 + npad / 4.0))
     batches = (rows + 6) // 7
-    issued = 2.0 * mac_tile * 8 * batches
-    common.update({
+    return 2.0 * mac_tile * 8 * batches, cyc_tile * 8, batches
+
+
+def roofline_tc(achieved, ffma_peak, flops_valid, k2_ms, share, rows, tc_status, sm_mhz):
+    """Roofline object of the dominant kernel (the fused network, tensor-core variant).  `achieved` is algorithmic:
+    valid-tap MACs x 2 per launch / mean launch time measured with CUDA events in the timed steps."""
+    pk = measured_peaks()
+    issued, cyc_batch, batches = tc_issue_model(rows)
+    ncu = ncu_figures("r02_k2tc_ncu.json", ["rced_net_tc.cu", "rced_tc.cuh"])
+    clk = (sm_mhz or 1965.0) * 1e6
+    r = {
         "bound": "tensor", "kernel": "rced_net_tc_kernel<2> (fused 16-layer network, tcgen05 kind::f16)",
-        "peak": pk["bf16_tflops"], "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", dense bf16/fp16",
-        "traffic": traffic,
-        "traffic_note": "dram__bytes_read + write of one launch (ncu --set full, profiles/k2tc_dram_traffic.json): 0.26 GB algorithmic, the "
-                        "rest is write-back of the L2-resident skip scratch",
-        "l1tex_throughput_pct": 91.0,
-        "l1tex_note": "ncu (profiles/r01_k2_tc_v7_ncu_digest.txt): l1tex__throughput 91 % of peak -- the shared-memory operand fetch "
-                      "of the small-N MMAs is the binding unit; sm__pipe_tensor_cycles_active 40 %",
+        "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
+        "peak_source": pk["source"] + ", dense bf16/fp16 (burst: the kernel is timed by its own events)",
+        "flops_per_launch": flops_valid, "flop_basis": "valid-tap MACs x2 (3,959,092 MAC/frame), FP32-equivalent",
+        "kernel_ms": k2_ms, "kernel_share_of_step": share,
+        "traffic": ncu.get("dram_bytes_per_launch") if ncu else None,
+        "ncu": ncu,
         "issued_tflops": issued / (k2_ms * 1e-3) / 1e12,
+        "issued_per_useful_flop": issued / flops_valid,
         "issued_note": "tensor-core FLOP actually issued: 3 FP16 products per multiply, channels padded to 8 / 16 / 32, "
                        "136-row frame stride, 7 frames per 8 row tiles",
         "fp32_ffma_peak": ffma_peak, "achieved_vs_fp32_ffma_peak": achieved / ffma_peak,
@@ -231,11 +257,31 @@ def roofline(variant, achieved, ffma_peak, flops_valid, k2_ms, share, traffic, r
             "note": "a small-N tcgen05.mma is bound by its shared-memory operand fetch (32 + N/4 cycles at M = 128, "
                     "profiles/r01_umma_probe_rates.log), not by the tensor pipe: the kernel's own ceiling is the sum of "
                     "those cycles",
-            "mma_cycles_per_batch": cyc_tile * 8,
-            "pipe_busy_frac": cyc_tile * 8 * batches / 148.0 / (k2_ms * 1e-3 * 1.965e9)},
+            "mma_cycles_per_batch": cyc_batch,
+            "pipe_busy_frac": cyc_batch * batches / 148.0 / (k2_ms * 1e-3 * clk)},
         "guard": tc_status,
-    })
-    return common
+    }
+    return r
+
+
+def roofline_ffma(achieved, ffma_peak, flops_valid, k2_ms):
+    ncu = ncu_figures("k2_dram_traffic.json", ["rced_net.cu"])
+    return {"bound": "fp32_ffma", "kernel": "rced_net_kernel<2,TMEM> (fused 16-layer network, FP32 FFMA2)", "achieved": achieved,
+            "peak": ffma_peak, "unit": "TFLOP/s", "frac": achieved / ffma_peak, "kernel_ms": k2_ms,
+            "flops_per_launch": flops_valid, "flop_basis": "valid-tap MACs x2 (3,959,092 MAC/frame)",
+            "traffic": ncu.get("dram_bytes_per_launch") if ncu else None,
+            "peak_source": "measured in this run by rced_ffma_peak (independent FFMA chains, 64 warps/SM); "
+                           "MEASURED_PEAKS.json holds no FP32 figure; nominal 2*128*148*1.965 GHz = 74.4"}
+
+
+def roofline_hbm(kernel, ms, rows, bytes_per_row, what, ncu_name, sources):
+    pk = measured_peaks()
+    algo = float(rows) * bytes_per_row
+    gbs = algo / (ms * 1e-3) / 1e9
+    ncu = ncu_figures(ncu_name, sources)
+    return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "kernel_ms": ms, "bytes_per_launch": algo, "byte_basis": what, "peak_source": pk["source"],
+            "traffic": ncu.get("dram_bytes_per_launch") if ncu else None, "ncu": ncu}
 
 
 _REAL_STDOUT = None
@@ -257,6 +303,44 @@ def emit(obj):
     out.flush()
 
 
+def latency_block(eng, pool, torch):
+    """Small-batch latencies through the host API (BASELINE.json configs[0] shape): one 4 s
+    utterance per call, and the online enhancer's push for 512- and 4096-sample blocks (look-back 13 hops + block +
+    look-ahead 6 hops per call).  Host wall clock around the synchronous call, median of the repetitions."""
+    from fullycnnspeechenhancement_b200.streaming import LOOK_AHEAD, LOOK_BACK, StreamingEnhancer
+    out = {}
+    wv = pool[0]
+    for _ in range(5):
+        eng.enhance([wv])
+    ts = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        eng.enhance([wv])
+        ts.append(time.perf_counter() - t0)
+    one = float(np.median(ts))
+    out["one_utterance_4s"] = {"ms": 1e3 * one, "real_time_factor": one / (UTT_SAMPLES / SAMPLE_RATE),
+                               "what": "Enhancer.enhance([4 s waveform]): numpy in, numpy out, one rced_enhance_host call"}
+    long_wv = np.concatenate([pool[i] for i in range(4)])
+    for block in (512, 4096):
+        st = StreamingEnhancer(eng, block=block)
+        ts = []
+        pos = 0
+        while pos + block <= len(long_wv) and len(ts) < 60:
+            t0 = time.perf_counter()
+            st.push(long_wv[pos:pos + block])
+            ts.append(time.perf_counter() - t0)
+            pos += block
+        st.flush()
+        push = float(np.median(ts[5:]))
+        out["stream_block_%d" % block] = {
+            "push_ms": 1e3 * push, "real_time_factor": push / (block / SAMPLE_RATE),
+            "algorithmic_latency_ms": 1e3 * (LOOK_AHEAD + block) / SAMPLE_RATE,
+            "samples_per_call": LOOK_BACK + block + LOOK_AHEAD,
+            "what": "StreamingEnhancer.push of one block (host wall clock, median); final samples lag the input by the "
+                    "look-ahead plus the block"}
+    return out
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -265,12 +349,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip-in-global", action="store_true", help="park skips in global scratch instead of TMEM")
     ap.add_argument("--variant", default=DEFAULT_VARIANT, choices=["ffma", "tc"],
-                    help="network kernel: FP32 FFMA, or tcgen05 tensor cores with the FP16 x3 split")
-    ap.add_argument("--sweep-utterances", type=int, default=0,
-                    help="also time one job of this many 4 s utterances partitioned over the ranks (BASELINE.json configs[4]: "
-                         "100000), device-resident, and report it under 'sweep'")
+                    help="network kernel behind `value` / `e2e`: tcgen05 tensor cores with the FP16 x3 split (default), or FP32 "
+                         "FFMA.  The other kernel is always timed for a few steps as well (`fp32_ffma` / `tensor_core`)")
+    ap.add_argument("--sweep-utterances", type=int, default=100000,
+                    help="one job of this many 4 s utterances partitioned over the ranks (BASELINE.json configs[4]), device-"
+                         "resident, reported under 'sweep' (0: skip)")
+    ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -299,40 +384,45 @@ def main():
     # random-init weights of the reference architecture (no checkpoint ships with the reference)
     weights = fold.glorot_weights(NET_WORK, seed=0)
     eng = Enhancer(NET_WORK, weights, device=local_rank, variant=args.variant)
-    if args.skip_in_global:
-        eng.set_skip_in_tmem(False)
     eng.set_variant(args.variant)
+    other = "ffma" if args.variant == "tc" else "tc"
 
     pool = synth_pool()
     lengths = np.full(N_UTT, UTT_SAMPLES, dtype=np.int64)
     total = int(lengths.sum())
-    h_wav = torch.empty(total, dtype=torch.float32).pin_memory()
-    hv = h_wav.numpy()
+    # two sets of page-locked host buffers: step i + 1 is queued while step i still runs (a consumer would read the
+    # other set meanwhile)
+    h_wav = [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_out = [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(2)]
+    hv = h_wav[0].numpy()
     for i in range(N_UTT):
         hv[i * UTT_SAMPLES:(i + 1) * UTT_SAMPLES] = pool[(i + rank) % POOL]
-    h_out = torch.empty(total, dtype=torch.float32).pin_memory()
-    d_wav = h_wav.to(dev)
+    h_wav[1].copy_(h_wav[0])
+    d_wav = h_wav[0].to(dev)
     d_out = torch.empty_like(d_wav)
 
     T = int(num_frames(UTT_SAMPLES))
     rows = N_UTT * T
     plan = eng.plan(lengths)                       # one chunk: the whole batch per launch
-    # pipelined over streams for the host path; a small first and last chunk shorten the first upload and the last
-    # download, which nothing overlaps
-    plan_e2e = eng.plan(lengths, chunk_utts=E2E_CHUNKS)
+    tables = eng.host_tables(lengths)
+    assert tables["total"] == total
     row_off = plan["row_off_all"]
     mag = torch.empty((rows, 129), dtype=torch.float32, device=dev)
     phase = torch.empty((rows, 129, 2), dtype=torch.float32, device=dev)
     pred = torch.empty((rows, 129), dtype=torch.float32, device=dev)
 
     def step_device(ev=None):
-        eng.stft_device(d_wav, plan["wav_off"], plan["wav_len"], row_off, rows, mag, phase)
         if ev:
             ev[0].record()
-        eng.forward_device(mag, row_off, pred)
+        eng.stft_device(d_wav, plan["wav_off"], plan["wav_len"], row_off, rows, mag, phase)
         if ev:
             ev[1].record()
+        eng.forward_device(mag, row_off, pred)
+        if ev:
+            ev[2].record()
         eng.istft_device(pred, phase, row_off, T, d_out, plan["wav_off"], plan["wav_len"])
+        if ev:
+            ev[3].record()
 
     def barrier():
         if world > 1:
@@ -345,6 +435,23 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def timed_device_steps(n_steps, n_warm):
+        """n_steps passes of K1 -> K2 -> K3 with CUDA events around every kernel; returns (ms total, [K1, K2, K3] mean ms)."""
+        for _ in range(n_warm):
+            step_device()
+        barrier()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_steps)]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for i in range(n_steps):
+            step_device(evs[i])
+        b.record()
+        barrier()
+        ms = max_over_ranks(a.elapsed_time(b))
+        per = [float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])) for j in range(3)]
+        return ms, per
 
     # measured FP32 FFMA peak of this GPU (the roofline denominator; MEASURED_PEAKS.json has none)
     tf = ctypes.c_double()
@@ -360,40 +467,50 @@ def main():
         sampler.start()
         time.sleep(0.25)
     launches0 = lib.rced_launch_count()
-    k2_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step_device(k2_events[i])
-    e1.record()
-    barrier()
+    ms_total, (k1_ms, k2_ms, k3_ms) = timed_device_steps(args.steps, 0)
     launches = lib.rced_launch_count() - launches0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    k2_ms = float(np.mean([a.elapsed_time(b) for a, b in k2_events]))
     audio_s_per_step = N_UTT * UTT_SAMPLES / SAMPLE_RATE
     value = world * audio_s_per_step * args.steps / (ms_total * 1e-3)
+    tc_status = None
+    if args.variant == "tc":
+        amax, perr = eng.tc_status()
+        tc_status = {"max_abs_activation_scaled_domain": amax, "protocol_error": perr,
+                     "ffma_fallback_ran": bool(not amax <= 65504.0 or perr != 0)}
 
-    # ---------------- end to end through the host API (`e2e`) ---------------------------------
-    for _ in range(max(1, min(args.warmup, 3))):
-        eng.run_plan_host(plan_e2e, h_wav, h_out, d_wav, d_out)
+    # ---------------- end to end through the host-buffer C entry point (`e2e`) -----------------
+    # rced_enhance_host_async: page-locked host waveforms -> H2D -> K1, K2, K3 -> D2H -> page-locked host output, chunked and
+    # pipelined over the library's streams; consecutive steps are queued behind each other (two buffer sets) and the
+    # timed region ends with rced_host_sync, so every step's copies are inside it.
+    def e2e_steps(n):
+        for i in range(n):
+            eng.enhance_host(h_wav[i & 1], h_out[i & 1], tables, sync=False)
+        eng.host_sync()
+
+    e2e_steps(max(2, min(args.warmup, 3)))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     f0.record()
-    for _ in range(args.steps):
-        eng.run_plan_host(plan_e2e, h_wav, h_out, d_wav, d_out)
+    t0 = time.perf_counter()
+    e2e_steps(args.steps)          # returns when the last step's output has arrived in host memory
+    wall = time.perf_counter() - t0
     f1.record()
     barrier()
-    e2e_ms = max_over_ranks(f0.elapsed_time(f1))
+    e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), wall * 1e3))
     e2e_value = world * audio_s_per_step * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---------------- the other network kernel, a few steps ------------------------------------
+    eng.set_variant(other)
+    o_steps = max(3, min(args.steps, 5))
+    o_ms_total, (_, o_k2_ms, _) = timed_device_steps(o_steps, 2)
+    o_value = world * audio_s_per_step * o_steps / (o_ms_total * 1e-3)
+    eng.set_variant(args.variant)
+
+    # ---------------- BASELINE.json configs[4]: one job partitioned across the ranks -----------
     sweep = None
     if args.sweep_utterances > 0:   # every rank takes part (before the non-zero ranks leave)
-        # BASELINE.json configs[4]: a fixed job partitioned across the ranks (strong scaling).  The job is cut into
-        # batches of N_UTT utterances (the device-resident pool tiled; H2D is not in the timed region), batch i goes to
-        # rank i % world, no collective.
+        # the job is cut into batches of N_UTT utterances (the device-resident pool tiled; H2D is not in the timed region),
+        # batch i goes to rank i % world, no collective
         n_batches = (args.sweep_utterances + N_UTT - 1) // N_UTT
         mine = len(range(rank, n_batches, world))
         step_device()
@@ -407,11 +524,10 @@ def main():
         job_ms = max_over_ranks(s0.elapsed_time(s1))
         job_utts = n_batches * N_UTT
         sweep = {"workload": "R-CED V2, one job of %d synthetic 4 s utterances (%d batches of %d) partitioned over %d "
-                                       "B200 (BASELINE.json configs[4]); inputs resident in HBM (pool tiled)" %
-                                       (job_utts, n_batches, N_UTT, world),
-                           "utterances": job_utts, "audio_seconds": job_utts * UTT_SAMPLES / SAMPLE_RATE,
-                           "job_seconds": job_ms * 1e-3, "scaling": "strong",
-                           "value": job_utts * UTT_SAMPLES / SAMPLE_RATE / (job_ms * 1e-3), "unit": UNIT}
+                             "B200 (BASELINE.json configs[4]); inputs resident in HBM (pool tiled)" % (job_utts, n_batches, N_UTT, world),
+                 "utterances": job_utts, "audio_seconds": job_utts * UTT_SAMPLES / SAMPLE_RATE, "n_gpus": world,
+                 "job_seconds": job_ms * 1e-3, "scaling": "strong", "network_kernel": args.variant,
+                 "value": job_utts * UTT_SAMPLES / SAMPLE_RATE / (job_ms * 1e-3), "unit": UNIT}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -419,21 +535,22 @@ def main():
 
     flops_valid = 2.0 * lib.rced_mac_per_frame(eng.arch, 1) * rows
     achieved = flops_valid / (k2_ms * 1e-3) / 1e12
-    tc_status = None
+    o_achieved = flops_valid / (o_k2_ms * 1e-3) / 1e12
+    share = k2_ms * args.steps / ms_total
+    sm_mhz = clocks.get("sm_mhz") if clocks else None
     if args.variant == "tc":
-        amax, perr = eng.tc_status()
-        tc_status = {"max_abs_activation": amax, "protocol_error": perr, "ffma_fallback_ran": bool(amax > 65504.0 or perr != 0)}
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "k2tc_dram_traffic.json" if args.variant == "tc" else "k2_dram_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except (ValueError, OSError):
-            traffic = None
+        main_roof = roofline_tc(achieved, ffma_peak, flops_valid, k2_ms, share, rows, tc_status, sm_mhz)
+        ffma_roof = roofline_ffma(o_achieved, ffma_peak, flops_valid, o_k2_ms)
+        ffma_value, ffma_steps = o_value, o_steps
+    else:
+        main_roof = roofline_ffma(achieved, ffma_peak, flops_valid, k2_ms)
+        main_roof["kernel_share_of_step"] = share
+        ffma_roof, ffma_value, ffma_steps = main_roof, value, args.steps
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16x3 (FP16 hi/lo split, 3 products per multiply, FP32 accumulate; 1e-6 of float64)" if args.variant == "tc" else "f32",
+        "dtype": "f16x3 (FP16 hi/lo split, 3 products per multiply, FP32 accumulate; scale-invariant, 1e-6 of float64)"
+                 if args.variant == "tc" else "f32",
         "data": "synthetic (64 seeded tone/chirp + white/babble-noise utterances tiled to 1024 per GPU)",
         "config": {"workload": "R-CED V2 (FullyCNNV2, 16 layers, random-init Glorot weights) batched enhancement of "
                                "1024 synthetic 4 s 8 kHz utterances per B200 (BASELINE.json configs[1])",
@@ -444,19 +561,32 @@ def main():
                    "network_kernel": "tcgen05 tensor cores, FP16 x3 error-compensated split (rced_net_tc_kernel); FP32 FFMA "
                                      "kernel queued behind it as range-guard fall-back" if args.variant == "tc"
                                      else "FP32 FFMA (rced_net_kernel)",
-                   "skip_storage": ("global scratch (L2)" if args.variant == "tc" else
-                                    "global" if args.skip_in_global else "tmem")},
+                   "skip_storage": "global scratch (L2), one region per resident CTA" if args.variant == "tc" else "tensor memory"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": total * 4,
-                "api": "Enhancer.run_plan_host: pinned host waveforms -> H2D -> rced_enhance (K1,K2,K3) -> D2H, "
-                       "chunks of %s utterances over 3 streams" % "/".join(str(c) for c in E2E_CHUNKS)},
+                "api": "rced_enhance_host_async (Enhancer.enhance_host): page-locked host waveforms -> H2D -> K1, K2, K3 -> D2H -> "
+                       "page-locked host output, chunks of ~32768 spectrogram rows over 3 library streams; the steps alternate "
+                       "between two host buffer sets and are queued behind each other, rced_host_sync closes the timed region "
+                       "(host wall clock)"},
         "gpu_launches": int(launches),
-        "roofline": roofline(args.variant, achieved, ffma_peak, flops_valid, k2_ms, k2_ms * args.steps / ms_total, traffic,
-                             rows, tc_status),
+        "roofline": main_roof,
+        # the metric BASELINE.json names for the network kernel: fraction of the FP32 FFMA peak reached by the FP32 kernel
+        "fp32_ffma": {"value": ffma_value, "unit": UNIT, "steps": ffma_steps, "roofline": ffma_roof,
+                      "what": "the same step with the FP32 FFMA network kernel (rced_net_kernel), device-resident"},
+        "roofline_k1": roofline_hbm("rced_stft_kernel", k1_ms, rows, 512 + 516 + 1032,
+                                    "512 B waveform in + 516 B magnitude + 1032 B phase out per frame (SURVEY.md 8d)",
+                                    "r02_k1_ncu.json", ["rced_stft.cu", "rced_fft.cuh"]),
+        "roofline_k3": roofline_hbm("rced_istft_kernel<512>", k3_ms, rows, 516 + 1032 + 512,
+                                    "516 B prediction + 1032 B phase in + 512 B waveform out per frame (SURVEY.md 8d)",
+                                    "r02_k3_ncu.json", ["rced_istft.cu", "rced_fft.cuh"]),
         "clocks": clocks,
     }
+    if args.variant != "tc":
+        result["tensor_core"] = {"value": o_value, "unit": UNIT, "steps": o_steps, "kernel_ms": o_k2_ms}
     if sweep is not None:
         result["sweep"] = sweep
+    if not args.no_latency and world == 1:
+        result["latency"] = latency_block(eng, pool, torch)
     if not args.no_cpu_baseline and world == 1:
         from oracle import network as onet
         result["cpu_baseline"] = cpu_baseline(pool, onet.random_weights(NET_WORK, seed=0, randomize_bn=False))

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librced_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 VARIANT_FFMA = 0   # FP32 FFMA network kernel
 VARIANT_TC = 1     # tcgen05 tensor-core kernel (FP16 x3 split)
 
@@ -45,6 +45,10 @@ SIGNATURES = {
     "rced_istft": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, c_i64, ctypes.c_int, c_p, c_p, c_p, c_p]),
     "rced_enhance": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, ctypes.c_int, c_i64, c_i64, ctypes.c_int,
                                     c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "rced_enhance_host": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_int, c_p, c_p, c_p]),
+    "rced_enhance_host_async": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_int, c_p, c_p, c_p]),
+    "rced_host_sync": (ctypes.c_int, [c_p]),
+    "rced_host_config": (ctypes.c_int, [c_p, ctypes.c_int, c_i64]),
     "rced_mag_phase": (ctypes.c_int, [ctypes.c_int, c_p, c_i64, c_p, c_p, c_p]),
     "rced_sdr_sums": (ctypes.c_int, [ctypes.c_int, c_p, c_p, c_p, c_p, c_p, ctypes.c_int, c_i64, c_p, c_p]),
     "rced_ffma_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),

@@ -6,10 +6,10 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
 mkdir -p build
 pids=()
-for f in rced_net rced_net_tc rced_stft rced_istft rced_api; do
+for f in rced_net rced_net_tc rced_stft rced_istft rced_api rced_host; do
   ( $NVCC $FLAGS -c $f.cu -o build/$f.o > build/$f.log 2>&1 || { cat build/$f.log; exit 1; } ) &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librced_b200.so build/rced_net.o build/rced_net_tc.o build/rced_stft.o build/rced_istft.o build/rced_api.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librced_b200.so build/rced_net.o build/rced_net_tc.o build/rced_stft.o build/rced_istft.o build/rced_api.o build/rced_host.o -lcudart
 echo "built $(cd .. && pwd)/librced_b200.so"

@@ -11,6 +11,7 @@
 
 #include "../../include/rced.h"
 #include "rced_arch.cuh"
+#include "rced_handle.h"
 #include "rced_internal.h"
 #include "rced_tc.cuh"
 
@@ -21,11 +22,11 @@ static std::atomic<long long> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-static int fail(int code, const std::string& msg) {
+int fail(int code, const std::string& msg) {
     t_err = msg;
     return code;
 }
-static int cuda_fail(cudaError_t e, const char* what) {
+int cuda_fail(cudaError_t e, const char* what) {
     return fail(RCED_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
 
@@ -232,50 +233,9 @@ static void pack_weights(int arch, const float* folded, float* packed) {
 
 using namespace rced;
 
-constexpr unsigned int kFlagRing = 4096;   // guard-flag pairs handed out round robin, one per tensor-core launch
-
-struct rced_handle {
-    int arch;
-    int device;
-    int num_sms;
-    bool skip_in_tmem;
-    float* d_packed;
-    // FFMA kernel with skips in global memory (rced_set_skip_in_tmem(h, 0)): num_sms regions + claim words
-    float* d_scratch;
-    unsigned int* d_scratch_busy;
-    // tensor-core variant (rced_net_tc.cu), allocated by rced_set_variant(h, RCED_VARIANT_TC)
-    int variant;
-    std::vector<float> folded;
-    unsigned char* d_tc_img;
-    float* d_tc_bias;
-    // The tensor-core kernel parks skip tensors in a global scratch of num_sms regions; a CTA claims a
-    // region when it starts (rced_slots.cuh), so launches that overlap on different streams share the
-    // one scratch.  Every launch reports through its own pair of guard-flag words, taken round robin
-    // from a ring (stream-ordered memset in front of the launch; a pair is reused after kFlagRing launches).
-    float* d_tc_skip;
-    unsigned int* d_tc_busy;
-    unsigned int* d_tc_flags;
-    std::atomic<unsigned int> tc_launches;
-    std::atomic<unsigned int*> last_tc_flags;
-    size_t tc_persist_bytes;       // > 0: launches carry an L2 access-policy window over the scratch
-    const char* trace_path;        // RCED_TC_TRACE (development aid), read once
-};
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        ok = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 extern "C" {
 
-int rced_abi_version(void) { return 2; }
+int rced_abi_version(void) { return 3; }
 const char* rced_last_error(void) { return t_err.c_str(); }
 
 int64_t rced_num_frames(int64_t n) {
@@ -370,6 +330,7 @@ int rced_create(int arch, const float* folded, size_t n_folded, int device, rced
     h->last_tc_flags = nullptr;
     h->tc_persist_bytes = 0;
     h->trace_path = getenv("RCED_TC_TRACE");
+    h->pipe = nullptr;
     if ((e = cudaMalloc(&h->d_packed, packed.size() * sizeof(float))) != cudaSuccess) {
         delete h;
         return cuda_fail(e, "cudaMalloc(weights)");
@@ -386,6 +347,7 @@ int rced_create(int arch, const float* folded, size_t n_folded, int device, rced
 void rced_destroy(rced_handle* h) {
     if (!h) return;
     DeviceGuard guard(h->device);
+    host_pipe_destroy(h->pipe);
     if (h->d_packed) cudaFree(h->d_packed);
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_scratch_busy) cudaFree(h->d_scratch_busy);

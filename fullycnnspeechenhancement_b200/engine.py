@@ -83,6 +83,8 @@ class Enhancer(object):
         self._h = h
         self._streams = None
         self._ws = {}
+        self._tables = {}
+        self._staging = None
         self.variant = "ffma"
         if variant == "tc":
             try:
@@ -257,24 +259,74 @@ class Enhancer(object):
         cur.synchronize()
         return h_out
 
-    # ------------------------------------------------------------------ convenience host API
-    def enhance(self, waveforms, chunk_utts=256):
-        """list of 1-D float waveforms (8 kHz) -> list of enhanced float32 waveforms of the same
-        lengths.  Equivalent to the reference's parse_audio -> power_spectrum/divide_phase ->
-        sess.run -> rebuild_audio chain (model_utils/tester.py:104-113) for each utterance."""
+    # ------------------------------------------------------------------ host-buffer API (C side owns the device)
+    def host_tables(self, lengths, out_lens=None, align=4):
+        """Offset tables of a packed batch in HOST memory for ``enhance_host``: utterance u occupies
+        ``wav[wav_off[u] : wav_off[u] + wav_len[u]]`` (starts aligned to ``align`` samples so that the STFT
+        kernel can use its vectorised loads) and its result goes to the same offset of the output buffer,
+        ``out_len[u]`` samples (default: the input length; the reference truncates to ``len(clean_sig[u])``,
+        model_utils/utils.py:181-182, at most the (T+1)*128 samples it rebuilds).  Cached for repeated shapes."""
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        if lengths.ndim != 1 or len(lengths) == 0:
+            raise ValueError("lengths must be a non-empty 1-D array")
+        if np.any(lengths < 1):
+            raise ValueError("every utterance needs at least one sample (the reference raises IndexError on L=0)")
+        key = (lengths.tobytes(), None if out_lens is None else np.asarray(out_lens, np.int64).tobytes(), align)
+        t = self._tables.get(key)
+        if t is None:
+            rebuilt = (num_frames(lengths) + 1) * FRAME_HOP
+            ol = lengths if out_lens is None else np.asarray(out_lens, dtype=np.int64)
+            ol = np.minimum(ol, rebuilt)          # numpy slicing [:L] never extends (utils.py:181-182)
+            span = (np.maximum(lengths, ol) + align - 1) // align * align
+            off = np.concatenate([[0], np.cumsum(span)[:-1]]).astype(np.int64)
+            t = {"n": len(lengths), "lengths": lengths, "wav_off": off, "wav_len": lengths.astype(np.int32),
+                 "out_off": off, "out_len": ol.astype(np.int32), "total": int(span.sum())}
+            if len(self._tables) >= 16:
+                self._tables.pop(next(iter(self._tables)))
+            self._tables[key] = t
+        return t
+
+    def enhance_host(self, h_wav, h_out, tables, sync=True):
+        """rced_enhance_host[_async]: waveforms in HOST memory in, enhanced waveforms in HOST memory out; the
+        library cuts the batch into chunks and pipelines copies and kernels over its own streams.  ``h_wav`` /
+        ``h_out``: float32 numpy arrays or CPU torch tensors laid out by ``tables`` (page-locked memory makes
+        the copies asynchronous).  With ``sync=False`` the call returns once the work is queued; ``h_out`` is
+        complete after ``host_sync()``."""
+        def addr(a):
+            return ctypes.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data)
+        f = self.lib.rced_enhance_host if sync else self.lib.rced_enhance_host_async
+        t = tables
+        _lib.check(f(self._h, addr(h_wav), addr(t["wav_off"]), addr(t["wav_len"]), t["n"], self.irfft_n,
+                     addr(h_out), addr(t["out_off"]), addr(t["out_len"])))
+        return h_out
+
+    def host_sync(self):
+        _lib.check(self.lib.rced_host_sync(self._h))
+
+    def host_config(self, n_streams=3, chunk_rows=32768):
+        _lib.check(self.lib.rced_host_config(self._h, int(n_streams), int(chunk_rows)))
+
+    def _stage(self, total):
+        """Persistent page-locked staging (input, output), grown geometrically: enhance() never pins per call."""
+        if self._staging is None or self._staging[0].numel() < total:
+            n = max(total + total // 4, 1 << 16)
+            self._staging = (torch.empty(n, dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory())
+        return self._staging
+
+    def enhance(self, waveforms, chunk_utts=None, out_lens=None):
+        """list of 1-D float waveforms (8 kHz) -> list of enhanced float32 waveforms of the same lengths
+        (or ``out_lens``).  Equivalent to the reference's parse_audio -> power_spectrum/divide_phase ->
+        sess.run -> rebuild_audio chain (model_utils/tester.py:104-113) for each utterance; one call of
+        rced_enhance_host.  ``chunk_utts`` is accepted for compatibility (the library chunks by rows)."""
         lengths = np.array([len(w) for w in waveforms], dtype=np.int64)
-        plan = self.plan(lengths, chunk_utts=chunk_utts)
-        total = plan["total_samples"]
-        h_wav = torch.empty(total, dtype=torch.float32).pin_memory()
-        hv = h_wav.numpy()
-        for w, o in zip(waveforms, plan["wav_off_host"]):
-            hv[o:o + len(w)] = np.asarray(w, dtype=np.float32)
-        h_out = torch.empty(total, dtype=torch.float32).pin_memory()
-        d_wav = torch.empty(total, dtype=torch.float32, device=self.device)
-        d_out = torch.empty(total, dtype=torch.float32, device=self.device)
-        self.run_plan_host(plan, h_wav, h_out, d_wav, d_out)
+        t = self.host_tables(lengths, out_lens)
+        h_in, h_out = self._stage(t["total"])
+        hv = h_in.numpy()
+        for w, o in zip(waveforms, t["wav_off"]):
+            hv[o:o + len(w)] = w
+        self.enhance_host(h_in, h_out, t, sync=True)
         ov = h_out.numpy()
-        return [ov[o:o + n].copy() for o, n in zip(plan["wav_off_host"], lengths)]
+        return [ov[o:o + n].copy() for o, n in zip(t["out_off"], t["out_len"])]
 
     def enhance_stream(self, waveform, chunk_seconds=4.0, sample_rate=8000):
         """Long-form enhancement in chunks (BASELINE config 4), equal to the un-chunked result up
@@ -299,6 +351,6 @@ class Enhancer(object):
             b = min(L, e + ahead)
             pieces.append(x[a:b])
             keep.append((s0 - a, e - a))
-        res = self.enhance(pieces, chunk_utts=64)
+        res = self.enhance(pieces)
         outs = [r[k0:k1] for r, (k0, k1) in zip(res, keep)]
         return np.concatenate(outs) if outs else np.zeros(0, np.float32)

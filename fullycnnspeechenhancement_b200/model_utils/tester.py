@@ -11,7 +11,7 @@ from .. import audio_io
 from ..config import section_with
 from . import fold
 from .model import build_model
-from .utils import SDR, AudioReBuild, AverageMeter, sdr_batch
+from .utils import PESQ, SDR, STOI, AudioReBuild, AverageMeter, sdr_batch
 
 
 class BaseTester(object):
@@ -77,25 +77,34 @@ class FullyCNNTester(BaseTester):
     def test(self, valid_loader):
         """The batch loop of tester.py:92-167.  Enhancement runs waveform -> waveform on the GPU
         (K1 -> K2 -> K3 from ``mix_sig``; the loader's complex batch is the same STFT and is not
-        needed).  SDR is scored; PESQ / STOI need third-party C libraries that are not installed
-        and stay at 0."""
-        sdr = SDR()
+        needed).  SDR (GPU energy sums) and STOI (numpy restatement of pystoi) are scored like the
+        reference does (tester.py:130-146); PESQ needs the ITU-T P.862 C code, which is not available:
+        it is printed as n/a, never as a number."""
+        Pesq = PESQ(sr=self.sample_rate)
+        Stoi = STOI(sr=self.sample_rate)
         eng = self.model.engine()
         for index, (batch_mix, batch_clean, mix_sig, clean_sig) in enumerate(valid_loader):
             start = time.time()
             audio_bins = valid_loader.bins[index]
-            denoise = eng.enhance(mix_sig)
-            denoise = [np.asarray(d[:len(c)], dtype=np.float64) for d, c in zip(denoise, clean_sig)]
+            # the reference rebuilds (T+1)*128 samples per utterance and truncates them to len(clean_sig[i])
+            # (tester.py:107-113, utils.py:181-182)
+            denoise = eng.enhance(mix_sig, out_lens=[len(c) for c in clean_sig])
+            denoise = [np.asarray(d, dtype=np.float64) for d in denoise]
             lens = [min(len(c), len(d)) for c, d in zip(clean_sig, denoise)]
             scores = sdr_batch([np.asarray(c[:n]) for c, n in zip(clean_sig, lens)], [d[:n] for d, n in zip(denoise, lens)],
                                device=eng.device.index)
             for i in range(len(audio_bins)):
                 self.sdr_score.update(float(scores[i]))
+                n = lens[i]
+                self.stoi_score.update(float(Stoi(np.asarray(clean_sig[i][:n], dtype=np.float64), denoise[i][:n])))
+                if Pesq.available:
+                    self.pesq_score.update(float(Pesq(np.asarray(clean_sig[i][:n]), denoise[i][:n])))
                 name = os.path.basename(valid_loader.dataset.item_name(audio_bins[i]))
                 audio_io.write_wav(os.path.join(self.audio_save_path, name), clean_sig[i], self.sample_rate)
                 audio_io.write_wav(os.path.join(self.audio_save_path, name.replace(".wav", "_mix.wav")), mix_sig[i], self.sample_rate)
                 audio_io.write_wav(os.path.join(self.audio_save_path, name.replace(".wav", "_de.wav")), denoise[i], self.sample_rate)
-            print("Testing %d  SDR=%.4f  BatchTime=%.3f" % (index, self.sdr_score.avg, time.time() - start))
-        print("Average p_score: {:.4f}; Average st_score: {:.4f}; Average sd_score: {:.4f}.\n".format(
-            self.pesq_score.avg, self.stoi_score.avg, self.sdr_score.avg))
+            print("Testing %d  STOI=%.4f  SDR=%.4f  BatchTime=%.3f" % (index, self.stoi_score.avg, self.sdr_score.avg, time.time() - start))
+        p_score = "{:.4f}".format(self.pesq_score.avg) if Pesq.available else "n/a (pypesq / ITU-T P.862 not available)"
+        print("Average p_score: {}; Average st_score: {:.4f}; Average sd_score: {:.4f}.\n".format(
+            p_score, self.stoi_score.avg, self.sdr_score.avg))
         return self.sdr_score.avg

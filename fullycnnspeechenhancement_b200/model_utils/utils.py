@@ -67,23 +67,35 @@ def sdr_batch(refs, ests, device=None):
     return 10 * np.log10(s[:, 0] / (s[:, 1] + np.finfo(np.float32).eps))
 
 
-class _Unavailable(object):
-    def __init__(self, name, sr=8000):
-        self.name = name
+class PESQ(object):
+    """The reference scores with ``pypesq.pesq`` (model_utils/utils.py:32-45): the ITU-T P.862 C implementation behind a
+    Python wrapper.  Neither the wrapper nor the ITU code is vendored in the reference or installed here, and the
+    standard's reference code cannot be restated from memory, so the score is reported as unavailable (``nan``) --
+    never as a number."""
+    available = False
 
-    def __call__(self, x, y):
-        raise ImportError("%s scoring needs the third-party package used by the reference, which is not "
-                          "installed; it is outside the enhancement forward path" % self.name)
+    def __init__(self, sr=16000):
+        self.sr = sr
+
+    def __call__(self, a, b):
+        assert len(a.shape) == 1
+        assert len(a) == len(b)
+        return float("nan")
 
 
-class PESQ(_Unavailable):
-    def __init__(self, sr=8000):
-        super(PESQ, self).__init__("PESQ (pypesq)", sr)
+class STOI(object):
+    """``pystoi.stoi(clean, processed, sr)`` of the reference (model_utils/utils.py:48-62), restated in numpy
+    (model_utils/stoi.py; pystoi itself is not installed)."""
+    available = True
 
+    def __init__(self, sr=16000):
+        self.sr = sr
 
-class STOI(_Unavailable):
-    def __init__(self, sr=8000):
-        super(STOI, self).__init__("STOI (pystoi)", sr)
+    def __call__(self, a, b):
+        from .stoi import stoi
+        assert len(a.shape) == 1
+        assert len(a) == len(b)
+        return stoi(a, b, self.sr)
 
 
 class AudioReBuild(object):

@@ -38,8 +38,10 @@ extern "C" {
 #define RCED_ARCH_V2 2       /* FullyCNNSEModelV2 (model_utils/model.py:32-61) */
 #define RCED_ARCH_V3 3       /* FullyCNNSEModelV3 (model_utils/model.py:64-96) */
 
-#define RCED_VARIANT_FFMA 0  /* FP32 FFMA network kernel (rced_net.cu), the default          */
-#define RCED_VARIANT_TC   1  /* tcgen05 tensor-core kernel, FP16 x3 error-compensated split  */
+#define RCED_VARIANT_FFMA 0  /* FP32 FFMA network kernel (rced_net.cu): what a new handle runs until    */
+                             /* rced_set_variant is called; exact FP32, the fall-back of the variant below */
+#define RCED_VARIANT_TC   1  /* tcgen05 tensor-core kernel, FP16 x3 error-compensated split: what the   */
+                             /* Python engine and bench.py select by default (3x faster, 1e-6 of float64) */
 
 #define RCED_OK 0
 #define RCED_ERR_ARG   (-1)
@@ -96,24 +98,29 @@ void rced_destroy(rced_handle* h);
 int rced_arch(const rced_handle* h);
 int rced_device(const rced_handle* h);
 
-/* 1 (default): skip-connection tensors are parked in Tensor Memory (tcgen05.st/ld);
- * 0: they go to a per-warp scratch area in global memory (L2 resident).  Both are
- * exercised by the parity tests. */
+/* FFMA kernel only.  1 (default): skip-connection tensors are parked in Tensor Memory (tcgen05.st/ld);
+ * 0: they go to a scratch in global memory (L2 resident) whose regions the CTAs claim when they start,
+ * so launches that overlap on several streams are safe.  Both are exercised by the parity tests. */
 int rced_set_skip_in_tmem(rced_handle* h, int enable);
 
 /* Network kernel behind rced_forward / rced_enhance (same call sites as K2 below:
  * model_utils/tester.py:85-90, infer.py:62-65).
- *   RCED_VARIANT_FFMA (default): register-tiled FP32 FFMA kernel.
+ *   RCED_VARIANT_FFMA (a new handle's setting): register-tiled FP32 FFMA kernel.
  *   RCED_VARIANT_TC: implicit-GEMM kernel on the 5th-generation tensor cores.  Activations and
  *     weights are split into FP16 hi + lo pairs (22 significant bits) and multiplied as
  *     hi*Whi + hi*Wlo + lo*Whi with FP32 accumulation; max relative error vs the float64 oracle
- *     is stated in tests/test_gpu_parity.py.  FP16 overflows beyond 65504: the kernel records the
- *     largest |activation| it stored and, stream-ordered, the FFMA kernel recomputes the call
- *     when that range was exceeded.  Refused (RCED_ERR_STATE) if a folded weight exceeds 65504. */
+ *     is stated in tests/test_gpu_tc.py.  The arithmetic is scale invariant: residuals are stored
+ *     times 2^11, every step's weights and every frame's activations live in power-of-two scaled
+ *     domains (csrc/rced_tc.cuh), so inputs and weights of any finite magnitude keep FP32-like
+ *     accuracy.  What remains is growth INSIDE the network: the kernel records the largest
+ *     |activation| it stored (scaled domain, limit 65504: 4000 x the frame's reference magnitude) and
+ *     whether an input was not finite, and, stream-ordered, the FFMA kernel recomputes the call when
+ *     that guard tripped.  Refused (RCED_ERR_STATE) only if a folded weight is not finite. */
 int rced_set_variant(rced_handle* h, int variant);
 int rced_variant(const rced_handle* h);
-/* Largest |activation| and protocol-error code of the last tensor-core launch (synchronises the
- * device; diagnostics and tests only). */
+/* Largest |activation| stored by the last tensor-core launch (in the frames' scaled domains; infinity:
+ * overflow or a non-finite input -> the FFMA kernel recomputed the call) and its protocol-error code
+ * (synchronises the device; diagnostics and tests only). */
 int rced_tc_status(rced_handle* h, float* max_abs, unsigned int* protocol_error);
 
 /* Host-side packing of the tensor-core kernel's weight image (FP16 hi/lo B-operand tiles per
@@ -121,7 +128,7 @@ int rced_tc_status(rced_handle* h, float* max_abs, unsigned int* protocol_error)
  * and arithmetic without a GPU.  rced_tc_layout writes: out[0]=steps, [1]=units, [2]=image bytes,
  * [3]=shared-memory bytes, [4]=plane stride (16-byte units), [5]=lead rows, [6]=rows per frame,
  * [7]=frames per batch, [8]=row tiles, [9]=offset of the lo planes (16-byte units), [10]=taps per
- * row-shifted block of the output layer, [11]=skip scratch floats per CTA, [12]=row-shifted blocks,
+ * row-shifted block of the output layer, [11]=skip scratch floats per region, [12]=row-shifted blocks,
  * [13]=zero rows in front of plane 0, [14..15]=0; then per step 6 values (units, first unit, NP, tile
  * bytes, image offset, is_final) and per unit 2 values (start offset and LBO of the A descriptor in
  * 16-byte units).  n >= 16 + 6*steps + 2*units. */
@@ -175,6 +182,33 @@ int rced_enhance(rced_handle* h, const float* wav, const int64_t* wav_off, const
                  const int64_t* row_off, int n_utt, int64_t total_rows, int64_t max_rows_per_utt,
                  int irfft_n, float* ws_mag, float* ws_phase, float* ws_pred,
                  float* out, const int64_t* out_off, const int32_t* out_len, void* stream);
+
+/* ---- host-buffer entry points ------------------------------------------------------- */
+
+/* The batch loop of the reference with HOST waveforms in and out: replaces
+ * parse_audio -> power_spectrum / divide_phase -> sess.run(pred) -> rebuild_audio
+ * (model_utils/tester.py:104-113, infer.py:54-71) for callers that hold numpy arrays.  The library owns
+ * the device side: the call is cut into chunks of utterances that are pipelined over a few internal
+ * streams (H2D, K1, K2, K3, D2H of different chunks overlap); device buffers belong to the handle and
+ * only grow.
+ *   wav      HOST float32, utterances concatenated (gaps allowed); page-locked memory makes the
+ *            copies asynchronous (pageable memory works, without overlap)
+ *   wav_off  HOST int64[n_utt] first sample of utterance u;  wav_len HOST int32[n_utt] (>= 1)
+ *   out      HOST float32; utterance u is written to out + out_off[u], out_len[u] samples
+ *            (out_len[u] <= (rced_num_frames(wav_len[u]) + 1) * 128; the reference truncates to
+ *            len(clean_sig[u]), model_utils/utils.py:181-182).  Gaps of fewer than 16 samples between
+ *            consecutive outputs are treated as alignment padding and may be overwritten; larger gaps
+ *            are left untouched (the outputs are then copied one by one)
+ * rced_enhance_host returns when `out` is complete.  rced_enhance_host_async returns once the work
+ * is queued -- the buffers must stay valid and `out` is complete after rced_host_sync(h); consecutive
+ * async calls pipeline behind each other.  rced_host_config: number of internal streams (1..4,
+ * default 3) and target spectrogram rows per chunk (default 32768). */
+int rced_enhance_host(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt,
+                      int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len);
+int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt,
+                            int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len);
+int rced_host_sync(rced_handle* h);
+int rced_host_config(rced_handle* h, int n_streams, int64_t chunk_rows);
 
 /* Element-wise |X| and X/|X| of `n` complex64 values (X == 0 -> phase 1+0j).  Replaces
  * AudioFeature.power_spectrum / divide_phase (data_utils/audio_feature.py:101-115) when the

@@ -196,3 +196,64 @@ def test_network_third_evaluator_scipy(arch):
         out = cbr(d, "decode_5", norm=False, act=False)
     ref = network.forward(arch, w, x[None, :, :, None], np.float64)[0, :, :, 0]
     assert np.abs(out[0] - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("arch", ["FullyCNN", "FullyCNNV2", "FullyCNNV3"])
+def test_network_fourth_evaluator_library_same_padding_and_batch_norm(arch):
+    """A fourth evaluation that does not hand-write what the three others share: the SAME padding is
+    ``torch.nn.functional.conv2d(padding='same')`` -- the library's own rule for even kernels (kh = 8: the extra row goes
+    behind, like TensorFlow's (k-1)//2 before) -- and the inference batch norm is ``F.batch_norm(training=False,
+    eps=1e-3)`` with the stored moving statistics, i.e. library code instead of the oracle's formula.  The graph is
+    written as the reference writes it (module.py:11-34: conv -> BN -> + skip -> ReLU; model.py for the wiring).
+    TensorFlow itself stays absent (parity unpinned): this removes the builder's reading of padding and BN
+    from the list of things all evaluators could share."""
+    import torch
+    import torch.nn.functional as F
+    w = network.random_weights(arch, seed=33, randomize_bn=True)
+    rng = np.random.default_rng(8)
+    T = 11
+    x = np.abs(rng.normal(0, 2, (2, T, 129, 1)))
+    tw = {k: torch.from_numpy(v).double() for k, v in w.items()}
+
+    def conv_bn_relu(t, scope, use_norm=True, use_act=True, skip_input=None):
+        k = tw[scope + "/kernel"].permute(3, 2, 0, 1).contiguous()          # HWIO -> OIHW
+        t = F.conv2d(t, k, tw[scope + "/bias"], stride=1, padding="same")
+        if use_norm:
+            t = F.batch_norm(t, tw[scope + "/batch_norm/moving_mean"], tw[scope + "/batch_norm/moving_variance"],
+                             tw[scope + "/batch_norm/gamma"], tw[scope + "/batch_norm/beta"], training=False, eps=1e-3)
+        if skip_input is not None:
+            t = t + skip_input
+        return torch.relu(t) if use_act else t
+
+    t = torch.from_numpy(x).double().permute(0, 3, 1, 2)                   # NHWC -> NCHW (H = time, W = frequency)
+    with torch.no_grad():
+        if arch == "FullyCNNV2":
+            enc = [t]
+            for i in range(1, 9):
+                enc.append(conv_bn_relu(enc[-1], "encode_%d" % i))
+            d = enc[8]
+            for i in range(1, 8):
+                d = conv_bn_relu(d, "decode_%d" % i, skip_input=enc[8 - i])
+            out = conv_bn_relu(d, "decode_8", use_norm=False, use_act=False)
+        elif arch == "FullyCNNV3":
+            def simple_rced(inp, name, skip=None):
+                e = conv_bn_relu(conv_bn_relu(conv_bn_relu(inp, name + "_encode_1"), name + "_encode_2"), name + "_decode")
+                return e if skip is None else e + skip
+            c1 = simple_rced(t, "CE1")
+            c2 = simple_rced(c1, "CE2")
+            c3 = simple_rced(c2, "CE3")
+            out = conv_bn_relu(simple_rced(simple_rced(c3, "CD1", c2), "CD2", c1), "decode_final", use_norm=False, use_act=False)
+        else:
+            e1 = conv_bn_relu(t, "encode_1")
+            e2 = conv_bn_relu(e1, "encode_2")
+            e3 = conv_bn_relu(e2, "encode_3")
+            e4 = conv_bn_relu(e3, "encode_4")
+            e5 = conv_bn_relu(e4, "encode_8")
+            d = conv_bn_relu(e5, "decode_1", skip_input=e4)
+            d = conv_bn_relu(d, "decode_2", skip_input=e3)
+            d = conv_bn_relu(d, "decode_3", skip_input=e2)
+            d = conv_bn_relu(d, "decode_4", skip_input=e1)
+            out = conv_bn_relu(d, "decode_5", use_norm=False, use_act=False)
+    got = out.permute(0, 2, 3, 1).numpy()
+    ref = network.forward(arch, w, x, np.float64)
+    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()

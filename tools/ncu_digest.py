@@ -1,5 +1,8 @@
 """Digest of an ncu report: key raw metrics of the first kernel plus the stall-sample breakdown
-by reason, opcode and code region (source page).  Usage: python tools/ncu_digest.py X.ncu-rep"""
+by reason, opcode and code region (source page).  Usage: python tools/ncu_digest.py X.ncu-rep
+       python tools/ncu_digest.py X.ncu-rep json <kernel name substring> <out.json> <csrc file> [<csrc file> ...]
+The json mode writes what bench.py reports next to a kernel's roofline (DRAM bytes per launch, the throughput of the
+units that bind it) together with the sha256 of the kernel sources the capture was taken from."""
 import collections
 import csv
 import io
@@ -7,8 +10,14 @@ import subprocess
 import sys
 
 
+KERNEL = None   # regex selecting one kernel of a report that holds several (argument `kernel=<regex>`)
+
+
 def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", name, "--csv"]
+    if KERNEL:
+        cmd += ["--kernel-name", "regex:" + KERNEL]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
@@ -112,7 +121,63 @@ def segments(rep, frames_per_warp_total):
     print("  loop bodies %.3f, once-per-layer code %.3f" % (loop, once))
 
 
+def to_json(rep, kernel_substr, out_path, sources):
+    import hashlib
+    import json
+    import os
+    rows = page(rep, "raw")
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    sel = [r for r in rows[2:] if kernel_substr in r[ix["Kernel Name"]]]
+    if not sel:
+        raise SystemExit("no kernel matching %r in %s" % (kernel_substr, rep))
+    r = sel[-1]
+
+    def val(name, scale_units=True):
+        if name not in ix or r[ix[name]] in ("", "n/a"):
+            return None
+        v = float(r[ix[name]].replace(",", ""))
+        if scale_units:
+            u = units[ix[name]].lower()
+            for pre, m in (("gbyte", 1e9), ("mbyte", 1e6), ("kbyte", 1e3), ("byte", 1.0), ("usecond", 1e-3), ("msecond", 1.0),
+                           ("nsecond", 1e-6), ("second", 1e3)):
+                if u.startswith(pre):
+                    return v * m
+        return v
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    for n in sources:
+        with open(os.path.join(root, "fullycnnspeechenhancement_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    d = {
+        "kernel": r[ix["Kernel Name"]], "report": os.path.basename(rep), "kernel_source_sha16": h.hexdigest()[:16],
+        "kernel_sources": list(sources),
+        "gpu_time_ms_under_ncu": val("gpu__time_duration.sum"),
+        "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": (rd or 0.0) + (wr or 0.0),
+        "dram_throughput_pct": val("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", False),
+        "l1tex_throughput_pct": val("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", False),
+        "lts_throughput_pct": val("lts__throughput.avg.pct_of_peak_sustained_elapsed", False),
+        "tensor_pipe_active_pct": val("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", False),
+        "fma_pipe_active_pct": val("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", False),
+        "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active", False),
+        "registers_per_thread": val("launch__registers_per_thread", False),
+        "warp_instructions": val("smsp__inst_executed.sum", False),
+    }
+    with open(out_path, "w") as f:
+        json.dump(d, f, indent=1)
+        f.write("\n")
+    print(json.dumps(d))
+
+
 if __name__ == "__main__":
+    for a in list(sys.argv):
+        if a.startswith("kernel="):
+            KERNEL = a[7:]
+            sys.argv.remove(a)
+    if len(sys.argv) > 5 and sys.argv[2] == "json":
+        to_json(sys.argv[1], sys.argv[3], sys.argv[4], sys.argv[5:])
+        sys.exit(0)
     if len(sys.argv) > 3 and sys.argv[2] == "segments":
         segments(sys.argv[1], float(sys.argv[3]))
         sys.exit(0)
