@@ -528,8 +528,15 @@ int rced_stft(rced_handle* h, const float* wav, const int64_t* wav_off, const in
     return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_stft launch");
 }
 
-int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n_utt, int64_t total_rows, float* pred,
-                 void* stream) {
+}  // extern "C"
+
+namespace rced {
+// rced_forward with the choice of what happens behind the tensor-core kernel: the FP32 kernel queued on the same
+// stream as the guard's fall-back (the C ABI's stream-ordered contract), or nothing -- the host pipeline checks the
+// launch's guard flags itself when it synchronises (*deferred_flags) and recomputes the rare chunk that tripped.
+int forward_impl(rced_handle* h, const float* mag, const int64_t* row_off, int n_utt, int64_t total_rows, float* pred,
+                 void* stream, unsigned int** deferred_flags) {
+    if (deferred_flags) *deferred_flags = nullptr;
     if (!h) return fail(RCED_ERR_ARG, "null handle");
     if (n_utt < 0 || total_rows < 0) return fail(RCED_ERR_ARG, "negative size");
     if (n_utt == 0 || total_rows == 0) return RCED_OK;
@@ -576,10 +583,22 @@ int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n
         }
         if (e != cudaSuccess) return cuda_fail(e, "rced_forward launch (tensor-core variant)");
         p.guard = d_flags;
+        if (deferred_flags) {
+            *deferred_flags = d_flags;
+            return RCED_OK;
+        }
     }
     e = launch_net(h->arch, h->skip_in_tmem, p, h->num_sms, (cudaStream_t)stream);
     count_launch();
     return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_forward launch");
+}
+}  // namespace rced
+
+extern "C" {
+
+int rced_forward(rced_handle* h, const float* mag, const int64_t* row_off, int n_utt, int64_t total_rows, float* pred,
+                 void* stream) {
+    return forward_impl(h, mag, row_off, n_utt, total_rows, pred, stream, nullptr);
 }
 
 int rced_istft(rced_handle* h, const float* pred, const float* phase, const int64_t* row_off, int n_utt,

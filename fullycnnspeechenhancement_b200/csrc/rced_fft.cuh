@@ -36,8 +36,30 @@ static inline cudaError_t upload_tables_local() {
     return cudaMemcpyToSymbol(g_tables, &host, sizeof(FftTables));
 }
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as ONE packed FP32 instruction (Blackwell FADD2): both kernels are bound by their issue slots
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    unsigned long long pa, pb, pd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pd) : "l"(pa), "l"(pb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(pd));
+    return d;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    unsigned long long pa, pb, pd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(pd) : "l"(pa), "l"(pb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(pd));
+    return d;
+}
+// The FFT leaves lane l with outputs 4 bitrev5(l) + b: stored as they are, the 32 lanes of a store hit 4 banks.
+// Two padding slots per 16 entries spread them over all banks, for the 16-byte stores of the transform's output as
+// well as for the consecutive 8-byte loads that follow.
+__device__ __forceinline__ int zpad(int e) { return e + 2 * (e >> 4); }
+constexpr int kZPad = 128 + 2 * 8;   // entries of a padded 128-point buffer
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }

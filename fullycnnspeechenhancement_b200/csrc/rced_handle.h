@@ -13,6 +13,12 @@ int fail(int code, const std::string& msg);          // records the calling thre
 int cuda_fail(cudaError_t e, const char* what);
 }  // namespace rced
 
+struct rced_handle;
+namespace rced {
+int forward_impl(rced_handle* h, const float* mag, const int64_t* row_off, int n_utt, int64_t total_rows, float* pred, void* stream,
+                 unsigned int** deferred_flags);
+}  // namespace rced
+
 constexpr unsigned int kFlagRing = 4096;   // guard-flag pairs handed out round robin, one per tensor-core launch
 
 struct rced_handle {

@@ -10,6 +10,14 @@
 // no allocation and no host synchronisation happens in steady state except the back-pressure on the
 // metadata ring (the host may run at most kMetaRing chunks ahead of a stream).
 //
+// Range guard of the tensor-core network kernel: the device-pointer ABI queues the FP32 kernel behind every
+// tensor-core launch (it returns at once unless the guard tripped).  Between the persistent launches of different
+// streams that kernel -- 148 CTAs that need most of an SM's shared memory -- has to wait for whole CTAs of the
+// neighbouring chunk to retire, which holds back the chunk's reconstruction and download.  The host pipeline
+// therefore copies each launch's guard words to page-locked memory instead and looks at them when it
+// synchronises: a chunk whose guard tripped (activations beyond the FP16 range, non-finite input: rare) is
+// recomputed from the caller's buffers with the FP32 kernel before the call returns.
+//
 // Caller's buffers: any host memory works (cudaMemcpyAsync); page-locked memory (cudaHostAlloc /
 // cudaHostRegister / torch pin_memory) is what makes the copies asynchronous and the chunks overlap.
 #include <cuda_runtime.h>
@@ -41,11 +49,29 @@ struct StreamCtx {
     unsigned int uses = 0;
 };
 
+constexpr int kPendingMax = 1024;   // chunks whose guard words wait for the next synchronisation
+
+struct PendingChunk {   // what is needed to recompute a chunk whose range guard tripped
+    const float* wav;
+    const int64_t* wav_off;
+    const int32_t* wav_len;
+    int c0, c1, irfft_n;
+    float* out;
+    const int64_t* out_off;
+    const int32_t* out_len;
+};
+
 struct HostPipe {
     int n_streams = 3;
-    int64_t chunk_rows = 32768;     // target spectrogram rows per chunk (about 130 four-second utterances)
+    // target spectrogram rows per chunk.  A synchronous call is cut finely (its first upload and last download
+    // overlap nothing, so they should be short); asynchronous calls pipeline behind each other and prefer few,
+    // large chunks (every chunk boundary is a gap in which the small kernels wait for persistent CTAs to retire).
+    int64_t chunk_rows = 49152, chunk_rows_async = 262144;
     StreamCtx s[kMaxStreams];
     unsigned int next_stream = 0;   // round robin across calls: consecutive small calls use different streams
+    unsigned int* h_flags = nullptr;   // page-locked [kPendingMax][2]: guard words of the pending tensor-core launches
+    std::vector<PendingChunk> pending;
+    bool recomputing = false;
 };
 
 static size_t grow(size_t need) { return need + need / 4 + 256; }
@@ -81,6 +107,7 @@ void host_pipe_destroy(HostPipe* p) {
         }
         if (c.stream) cudaStreamDestroy(c.stream);
     }
+    if (p->h_flags) cudaFreeHost(p->h_flags);
     delete p;
 }
 
@@ -95,6 +122,12 @@ static int pipe_get(rced_handle* h, HostPipe** out) {
                 return cuda_fail(e, "host pipeline: stream / event creation");
             }
         }
+        cudaError_t e = cudaHostAlloc(&p->h_flags, sizeof(unsigned int) * 2 * kPendingMax, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            host_pipe_destroy(p);
+            return cuda_fail(e, "host pipeline: pinned guard words");
+        }
+        p->pending.reserve(kPendingMax);
         h->pipe = p;
     }
     *out = h->pipe;
@@ -145,7 +178,7 @@ static int run_chunk(rced_handle* h, StreamCtx& c, const float* wav, const int64
     }
     if (meta_bytes > c.cap_meta) {
         cudaStreamSynchronize(c.stream);   // the old tables may still be read by queued work
-        const size_t nb = grow(meta_bytes);
+        const size_t nb = (grow(meta_bytes) + 255) & ~(size_t)255;   // every ring slot starts 256-byte aligned
         cudaFree(c.d_meta);
         c.d_meta = nullptr;
         for (int i = 0; i < kMetaRing; ++i) {
@@ -184,10 +217,23 @@ static int run_chunk(rced_handle* h, StreamCtx& c, const float* wav, const int64
         return cuda_fail(e, "host pipeline: H2D waveforms");
     if ((e = cudaMemcpyAsync(dm, hm, meta_bytes, cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return cuda_fail(e, "host pipeline: H2D tables");
     cudaEventRecord(c.meta_used[slot], c.stream);
-    const int rc = rced_enhance(h, c.d_wav, reinterpret_cast<const int64_t*>(dm + o_wav_off), reinterpret_cast<const int32_t*>(dm + o_wav_len),
-                                reinterpret_cast<const int64_t*>(dm + o_row_off), n, rows, max_rows, irfft_n, c.ws_mag, c.ws_phase, c.ws_pred,
-                                c.d_out, reinterpret_cast<const int64_t*>(dm + o_out_off), reinterpret_cast<const int32_t*>(dm + o_out_len),
-                                c.stream);
+    const int64_t* d_wav_off = reinterpret_cast<const int64_t*>(dm + o_wav_off);
+    const int64_t* d_row_off = reinterpret_cast<const int64_t*>(dm + o_row_off);
+    const int64_t* d_out_off = reinterpret_cast<const int64_t*>(dm + o_out_off);
+    const int32_t* d_wav_len = reinterpret_cast<const int32_t*>(dm + o_wav_len);
+    const int32_t* d_out_len = reinterpret_cast<const int32_t*>(dm + o_out_len);
+    int rc = rced_stft(h, c.d_wav, d_wav_off, d_wav_len, d_row_off, n, rows, c.ws_mag, c.ws_phase, c.stream);
+    if (rc != RCED_OK) return rc;
+    HostPipe* pipe = h->pipe;
+    unsigned int* d_flags = nullptr;
+    rc = forward_impl(h, c.ws_mag, d_row_off, n, rows, c.ws_pred, c.stream, pipe->recomputing ? nullptr : &d_flags);
+    if (rc != RCED_OK) return rc;
+    if (d_flags) {   // tensor-core launch: its guard words travel to the host behind it, the chunk is remembered
+        e = cudaMemcpyAsync(pipe->h_flags + 2 * pipe->pending.size(), d_flags, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "host pipeline: D2H guard words");
+        pipe->pending.push_back(PendingChunk{wav, wav_off, wav_len, c0, c1, irfft_n, out, out_off, out_len});
+    }
+    rc = rced_istft(h, c.ws_pred, c.ws_phase, d_row_off, n, max_rows, irfft_n, c.d_out, d_out_off, d_out_len, c.stream);
     if (rc != RCED_OK) return rc;
     if (out_contiguous) {
         e = cudaMemcpyAsync(out + o_lo, c.d_out, (size_t)(o_hi - o_lo) * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
@@ -215,11 +261,41 @@ int rced_host_config(rced_handle* h, int n_streams, int64_t chunk_rows) {
     if (rc != RCED_OK) return rc;
     p->n_streams = n_streams;
     p->chunk_rows = chunk_rows;
+    p->chunk_rows_async = chunk_rows;
     return RCED_OK;
 }
 
-int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt, int irfft_n,
-                            float* out, const int64_t* out_off, const int32_t* out_len) {
+static int host_sync_impl(rced_handle* h) {
+    HostPipe* p = h->pipe;
+    if (!p) return RCED_OK;
+    for (int i = 0; i < kMaxStreams; ++i) {
+        cudaError_t e = cudaStreamSynchronize(p->s[i].stream);
+        if (e != cudaSuccess) return cuda_fail(e, "rced_host_sync");
+    }
+    // range guard of the tensor-core launches since the last synchronisation (see the head of this file)
+    int rc = RCED_OK;
+    const std::vector<PendingChunk> pend = p->pending;
+    p->pending.clear();
+    for (size_t i = 0; i < pend.size() && rc == RCED_OK; ++i) {
+        const unsigned int amax = p->h_flags[2 * i], perr = p->h_flags[2 * i + 1];
+        if (amax <= 0x477FE000u /* 65504.0f */ && perr == 0u) continue;
+        const PendingChunk& q = pend[i];
+        const int variant = h->variant;
+        h->variant = RCED_VARIANT_FFMA;
+        p->recomputing = true;
+        rc = run_chunk(h, p->s[0], q.wav, q.wav_off, q.wav_len, q.c0, q.c1, q.irfft_n, q.out, q.out_off, q.out_len);
+        p->recomputing = false;
+        h->variant = variant;
+        if (rc == RCED_OK) {
+            cudaError_t e = cudaStreamSynchronize(p->s[0].stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "rced_host_sync (FP32 recomputation)");
+        }
+    }
+    return rc;
+}
+
+static int enhance_host_impl(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt, int irfft_n,
+                             float* out, const int64_t* out_off, const int32_t* out_len, bool async) {
     if (!h) return fail(RCED_ERR_ARG, "null handle");
     if (n_utt < 0) return fail(RCED_ERR_ARG, "negative size");
     if (irfft_n != 512 && irfft_n != 256) return fail(RCED_ERR_ARG, "irfft_n must be 512 or 256");
@@ -235,18 +311,19 @@ int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav
     HostPipe* p = nullptr;
     int rc = pipe_get(h, &p);
     if (rc != RCED_OK) return rc;
-    // chunks of about chunk_rows spectrogram rows; the first and the last chunk of a long call are a quarter of that:
-    // nothing overlaps the first upload and the last download
+    // chunks of about `target_rows` spectrogram rows; the first and the last chunk of a long synchronous call are a
+    // quarter of that: nothing overlaps the first upload and the last download
+    const int64_t chunk_rows = async ? p->chunk_rows_async : p->chunk_rows;
     std::vector<int> bounds;
     bounds.push_back(0);
     int64_t total_rows = 0;
     for (int u = 0; u < n_utt; ++u) total_rows += rced_num_frames(wav_len[u]);
-    const bool many = total_rows > 2 * p->chunk_rows;
+    const bool many = !async && total_rows > 2 * chunk_rows;
     int64_t acc = 0, done = 0;
     for (int u = 0; u < n_utt; ++u) {
         acc += rced_num_frames(wav_len[u]);
-        int64_t target = p->chunk_rows;
-        if (many && (bounds.size() == 1 || total_rows - done - acc < p->chunk_rows / 4)) target = p->chunk_rows / 4;
+        int64_t target = chunk_rows;
+        if (many && (bounds.size() == 1 || total_rows - done - acc < chunk_rows / 4)) target = chunk_rows / 4;
         if (acc >= target || u == n_utt - 1) {
             bounds.push_back(u + 1);
             done += acc;
@@ -254,6 +331,10 @@ int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav
         }
     }
     for (size_t i = 0; i + 1 < bounds.size(); ++i) {
+        if (p->pending.size() >= (size_t)kPendingMax) {   // the guard-word staging is full: drain
+            rc = host_sync_impl(h);
+            if (rc != RCED_OK) return rc;
+        }
         StreamCtx& c = p->s[p->next_stream++ % (unsigned int)p->n_streams];
         rc = run_chunk(h, c, wav, wav_off, wav_len, bounds[i], bounds[i + 1], irfft_n, out, out_off, out_len);
         if (rc != RCED_OK) return rc;
@@ -261,20 +342,21 @@ int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav
     return RCED_OK;
 }
 
+int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt, int irfft_n,
+                            float* out, const int64_t* out_off, const int32_t* out_len) {
+    return enhance_host_impl(h, wav, wav_off, wav_len, n_utt, irfft_n, out, out_off, out_len, true);
+}
+
 int rced_host_sync(rced_handle* h) {
     if (!h) return fail(RCED_ERR_ARG, "null handle");
     if (!h->pipe) return RCED_OK;
     DeviceGuard guard(h->device);
-    for (int i = 0; i < kMaxStreams; ++i) {
-        cudaError_t e = cudaStreamSynchronize(h->pipe->s[i].stream);
-        if (e != cudaSuccess) return cuda_fail(e, "rced_host_sync");
-    }
-    return RCED_OK;
+    return host_sync_impl(h);
 }
 
 int rced_enhance_host(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt, int irfft_n, float* out,
                       const int64_t* out_off, const int32_t* out_len) {
-    const int rc = rced_enhance_host_async(h, wav, wav_off, wav_len, n_utt, irfft_n, out, out_off, out_len);
+    const int rc = enhance_host_impl(h, wav, wav_off, wav_len, n_utt, irfft_n, out, out_off, out_len, false);
     if (rc != RCED_OK) return rc;
     return rced_host_sync(h);
 }

@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(kIstftWarps * 32) rced_istft_kernel(const Istf
     __shared__ float2 s_tw512[132];
     __shared__ float s_iham[256];
     __shared__ float2 s_y[kIstftWarps][132];
-    __shared__ float2 s_ze[kIstftWarps][128];
-    __shared__ float2 s_zo[kIstftWarps][128];
+    __shared__ __align__(16) float2 s_ze[kIstftWarps][kZPad];
+    __shared__ __align__(16) float2 s_zo[kIstftWarps][kZPad];
     __shared__ float s_wend[2][kIstftWarps];
 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -121,25 +121,26 @@ __global__ void __launch_bounds__(kIstftWarps * 32) rced_istft_kernel(const Istf
             }
             fft128_warp<true>(ze, lane, s_tw);
             if (N512) fft128_warp<true>(zo, lane, s_tw);
-            const int k0 = 4 * bitrev5(lane);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                s_ze[warp][k0 + b] = ze[b];
-                if (N512) s_zo[warp][k0 + b] = zo[b];
+            const int k0 = zpad(4 * bitrev5(lane));   // (a run of four never crosses a padding step)
+            *reinterpret_cast<float4*>(&s_ze[warp][k0]) = make_float4(ze[0].x, ze[0].y, ze[1].x, ze[1].y);
+            *reinterpret_cast<float4*>(&s_ze[warp][k0 + 2]) = make_float4(ze[2].x, ze[2].y, ze[3].x, ze[3].y);
+            if (N512) {
+                *reinterpret_cast<float4*>(&s_zo[warp][k0]) = make_float4(zo[0].x, zo[0].y, zo[1].x, zo[1].y);
+                *reinterpret_cast<float4*>(&s_zo[warp][k0 + 2]) = make_float4(zo[2].x, zo[2].y, zo[3].x, zo[3].y);
             }
             __syncwarp();
             const int m0 = 128 * half + 4 * lane;      // position inside the 256-sample frame
             if (N512) {
                 // y[4n..4n+3] = (Re ze[n], Re zo[n], Im ze[n], Im zo[n]) / 256
                 const int n = 32 * half + lane;
-                const float2 e = s_ze[warp][n], o = s_zo[warp][n];
+                const float2 e = s_ze[warp][zpad(n)], o = s_zo[warp][zpad(n)];
                 v = make_float4(e.x, o.x, e.y, o.y);
                 const float sc256 = 1.f / 256.f;
                 v.x *= sc256; v.y *= sc256; v.z *= sc256; v.w *= sc256;
             } else {
                 // y[2n] = Re z[n] / 128, y[2n+1] = Im z[n] / 128
                 const int n = 64 * half + 2 * lane;
-                const float2 e = s_ze[warp][n], o = s_ze[warp][n + 1];
+                const float2 e = s_ze[warp][zpad(n)], o = s_ze[warp][zpad(n + 1)];
                 const float sc128 = 1.f / 128.f;
                 v = make_float4(e.x * sc128, e.y * sc128, o.x * sc128, o.y * sc128);
             }

@@ -23,7 +23,7 @@ __device__ __forceinline__ long long frames_of(long long L) {   // audio_feature
 __global__ void __launch_bounds__(kStftWarps * 32) rced_stft_kernel(const StftParams p) {
     __shared__ float2 s_tw[256];
     __shared__ float s_ham[256];
-    __shared__ float2 s_z[kStftWarps][128];
+    __shared__ __align__(16) float2 s_z[kStftWarps][kZPad];
 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         s_tw[i] = g_tables.tw256[i];
@@ -66,41 +66,73 @@ __global__ void __launch_bounds__(kStftWarps * 32) rced_stft_kernel(const StftPa
             continue;
         }
 
-        const float* __restrict__ s = p.wav + __ldg(p.wav_off + u);
+        const long long woff = __ldg(p.wav_off + u);
+        const float* __restrict__ s = p.wav + woff;
         float2 v[4];
+        if (((woff | (long long)(uintptr_t)p.wav >> 2) & 1) == 0 && 128 * t + 256 <= L) {
+            // Frame inside the signal, sample pairs 8-byte aligned: four coalesced 8-byte loads per lane (256
+            // contiguous bytes per warp instruction); the sample in front of a pair comes from the neighbouring
+            // lane, only lane 0 reads the one in front of the frame.
+            const float2* __restrict__ s2 = reinterpret_cast<const float2*>(s + 128 * t);
+            float2 q[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int n = lane + 32 * a;
-            const long long i0 = 128 * t + 2 * n;
-            const float sm = (i0 >= 1 && i0 - 1 < L) ? __ldg(s + i0 - 1) : 0.f;
-            const float s0 = (i0 < L) ? __ldg(s + i0) : 0.f;
-            const float s1 = (i0 + 1 < L) ? __ldg(s + i0 + 1) : 0.f;
-            // audio_feature.py:54 in float32 without contraction; zero padding is appended AFTER
-            // the emphasis (audio_feature.py:71-73), so samples >= L are exactly 0
-            float e0 = (i0 == 0) ? s0 : __fsub_rn(s0, __fmul_rn(0.97f, sm));
-            float e1 = __fsub_rn(s1, __fmul_rn(0.97f, s0));
-            if (i0 >= L) e0 = 0.f;
-            if (i0 + 1 >= L) e1 = 0.f;
-            v[a] = make_float2(e0 * s_ham[2 * n], e1 * s_ham[2 * n + 1]);
+            for (int a = 0; a < 4; ++a) q[a] = __ldg(s2 + lane + 32 * a);
+            float edge = 0.f;
+            if (lane == 0 && t > 0) edge = __ldg(s + 128 * t - 1);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int n = lane + 32 * a;
+                float sm = __shfl_up_sync(0xffffffffu, q[a].y, 1);
+                const float wrap = __shfl_sync(0xffffffffu, a > 0 ? q[a > 0 ? a - 1 : 0].y : edge, a > 0 ? 31 : 0);
+                if (lane == 0) sm = wrap;
+                // audio_feature.py:54 in float32 without contraction
+                const float e0 = (a == 0 && lane == 0 && t == 0) ? q[a].x : __fsub_rn(q[a].x, __fmul_rn(0.97f, sm));
+                const float e1 = __fsub_rn(q[a].y, __fmul_rn(0.97f, q[a].x));
+                const float2 hw = *reinterpret_cast<const float2*>(s_ham + 2 * n);
+                v[a] = make_float2(e0 * hw.x, e1 * hw.y);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int n = lane + 32 * a;
+                const long long i0 = 128 * t + 2 * n;
+                const float sm = (i0 >= 1 && i0 - 1 < L) ? __ldg(s + i0 - 1) : 0.f;
+                const float s0 = (i0 < L) ? __ldg(s + i0) : 0.f;
+                const float s1 = (i0 + 1 < L) ? __ldg(s + i0 + 1) : 0.f;
+                // audio_feature.py:54 in float32 without contraction; zero padding is appended AFTER
+                // the emphasis (audio_feature.py:71-73), so samples >= L are exactly 0
+                float e0 = (i0 == 0) ? s0 : __fsub_rn(s0, __fmul_rn(0.97f, sm));
+                float e1 = __fsub_rn(s1, __fmul_rn(0.97f, s0));
+                if (i0 >= L) e0 = 0.f;
+                if (i0 + 1 >= L) e1 = 0.f;
+                v[a] = make_float2(e0 * s_ham[2 * n], e1 * s_ham[2 * n + 1]);
+            }
         }
         fft128_warp<false>(v, lane, s_tw);
-        const int k0 = 4 * bitrev5(lane);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) s_z[warp][k0 + b] = v[b];
+        const int k0 = zpad(4 * bitrev5(lane));   // (a run of four never crosses a padding step)
+        *reinterpret_cast<float4*>(&s_z[warp][k0]) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+        *reinterpret_cast<float4*>(&s_z[warp][k0 + 2]) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
         __syncwarp();
+        // split step: X_k = E_k + W^k O_k from Z_k and Z_{128-k}; |X| and X / |X| with one reciprocal square root
 #pragma unroll
-        for (int a = 0; a < 5; ++a) {
-            const int k = a < 4 ? lane + 32 * a : 128;
-            if (a == 4 && lane != 0) break;
-            const float2 zk = s_z[warp][k & 127];
-            const float2 zn = cconj(s_z[warp][(128 - k) & 127]);
+        for (int a = 0; a < 4; ++a) {
+            const int k = lane + 32 * a;
+            const float2 zk = s_z[warp][zpad(k)];
+            const float2 zn = cconj(s_z[warp][zpad((128 - k) & 127)]);
             const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y));
             const float2 d = csub(zk, zn);
             const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);   // -i/2 * d
             const float2 x = cadd(e, cmul(s_tw[k], o));
-            const float m = sqrtf(fmaf(x.x, x.x, x.y * x.y));
-            mag[k] = m;
-            if (ph) ph[k] = m > 0.f ? make_float2(x.x / m, x.y / m) : make_float2(1.f, 0.f);
+            const float m2 = fmaf(x.x, x.x, x.y * x.y);
+            const float inv = rsqrtf(m2);                            // (+inf at 0: not used there)
+            mag[k] = m2 > 0.f ? m2 * inv : 0.f;
+            if (ph) ph[k] = m2 > 0.f ? make_float2(x.x * inv, x.y * inv) : make_float2(1.f, 0.f);
+        }
+        if (lane == 0) {   // bin 128 is real: X_128 = Re Z_0 - Im Z_0
+            const float2 z0 = s_z[warp][0];
+            const float x = z0.x - z0.y;
+            mag[128] = fabsf(x);
+            if (ph) ph[128] = make_float2(x < 0.f ? -1.f : 1.f, 0.f);   // exp(j angle(X)): +-1 (1 at X = 0)
         }
         __syncwarp();
     }

@@ -200,9 +200,13 @@ int rced_enhance(rced_handle* h, const float* wav, const int64_t* wav_off, const
  *            consecutive outputs are treated as alignment padding and may be overwritten; larger gaps
  *            are left untouched (the outputs are then copied one by one)
  * rced_enhance_host returns when `out` is complete.  rced_enhance_host_async returns once the work
- * is queued -- the buffers must stay valid and `out` is complete after rced_host_sync(h); consecutive
- * async calls pipeline behind each other.  rced_host_config: number of internal streams (1..4,
- * default 3) and target spectrogram rows per chunk (default 32768). */
+ * is queued -- the buffers AND the offset / length arrays must stay valid and `out` is complete after
+ * rced_host_sync(h); consecutive async calls pipeline behind each other.  With the tensor-core
+ * variant the range guard is evaluated at the synchronisation: a chunk whose guard tripped is
+ * recomputed with the FP32 kernel before rced_host_sync / rced_enhance_host returns.
+ * rced_host_config: number of internal streams (1..4, default 3) and target spectrogram rows per
+ * chunk (defaults: 49152 for the synchronous call, whose first and last chunk are a quarter of that,
+ * 262144 for asynchronous calls). */
 int rced_enhance_host(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt,
                       int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len);
 int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt,

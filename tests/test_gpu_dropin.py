@@ -182,3 +182,87 @@ def test_sdr_batch_matches_the_reference_formula():
     assert got.shape == (5,) and np.all(np.isfinite(got))
     assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
     assert sdr_batch([], []).shape == (0,)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-buffer C entry points (rced_enhance_host / rced_enhance_host_async / rced_host_sync)
+# ---------------------------------------------------------------------------------------------------------------
+def _host_eng(seed=77):
+    from fullycnnspeechenhancement_b200.engine import Enhancer
+    from oracle import network
+    w = network.random_weights("FullyCNNV2", seed=seed, randomize_bn=True)
+    return Enhancer("FullyCNNV2", w, device=0), w
+
+
+def test_host_entry_point_equals_the_device_path():
+    """rced_enhance_host (numpy in, numpy out, chunked over the library's streams) against the device-pointer path
+    (rced_stft -> rced_forward -> rced_istft on caller-owned tensors), for ragged lengths, several chunks per call,
+    asynchronous calls queued behind each other, and out_len shorter than the input.  The two paths pack the frames
+    differently, and the tensor-core kernel's output layer sums its 32-tap diagonals in an order that depends on a
+    row's position in its 32-row block: equal to FP32 rounding (>= 120 dB), not bit for bit; the same packing twice is
+    bit-identical."""
+    import torch
+    from fullycnnspeechenhancement_b200.synth import noisy_utterance
+    eng, _ = _host_eng()
+    rng = np.random.default_rng(3)
+    lens = [int(x) for x in rng.integers(200, 9000, 37)] + [1, 255, 256, 257]
+    waves = [noisy_utterance(500 + i, n) for i, n in enumerate(lens)]
+    eng.host_config(n_streams=3, chunk_rows=300)            # many chunks per call
+    outs = eng.enhance(waves)
+    # device path on the same packed batch
+    plan = eng.plan(np.array(lens))
+    d_wav = torch.from_numpy(np.concatenate(waves)).to(eng.device)
+    d_out = torch.zeros_like(d_wav)
+    eng.run_plan_device(plan, d_wav, d_out)
+    torch.cuda.synchronize()
+    ref = d_out.cpu().numpy()
+    for o, off, n in zip(outs, plan["wav_off_host"], lens):
+        r = ref[off:off + n].astype(np.float64)
+        assert len(o) == n and np.sum((o - r) ** 2) <= 1e-12 * max(np.sum(r ** 2), 1e-30)
+    # asynchronous calls on two buffer sets, one synchronisation
+    t = eng.host_tables(np.array(lens))
+    bufs = []
+    for k in range(3):
+        h_in = np.zeros(t["total"], np.float32)
+        for w, o in zip(waves, t["wav_off"]):
+            h_in[o:o + len(w)] = w
+        h_out = np.full(t["total"], -7.0, np.float32)
+        bufs.append((h_in, h_out))
+        eng.enhance_host(h_in, h_out, t, sync=False)
+    eng.host_sync()
+    for h_in, h_out in bufs:
+        for o, n, r in zip(t["out_off"], lens, outs):
+            assert np.array_equal(h_out[o:o + n], r)
+    # truncated outputs (the reference cuts to len(clean_sig)): nothing behind out_len is written when the gap is large
+    cut = [max(1, n - 40) for n in lens]
+    t2 = eng.host_tables(np.array(lens), out_lens=cut)
+    h_out = np.full(t2["total"], -7.0, np.float32)
+    eng.enhance_host(bufs[0][0], h_out, t2, sync=True)
+    for o, n, c, r in zip(t2["out_off"], lens, cut, outs):
+        assert np.array_equal(h_out[o:o + c], r[:c])
+        if n - c >= 16 + 3:
+            assert np.all(h_out[o + c + 16:o + n] == -7.0)
+    eng.close()
+
+
+def test_host_entry_point_recomputes_a_tripped_chunk_with_the_fp32_kernel():
+    """The host pipeline checks the tensor-core launches' guard words when it synchronises and recomputes a tripped chunk
+    from the caller's buffers with the FP32 kernel: the result equals the FP32 engine's."""
+    from fullycnnspeechenhancement_b200.engine import Enhancer
+    from fullycnnspeechenhancement_b200.synth import noisy_utterance
+    from oracle import network
+    w = network.random_weights("FullyCNNV2", seed=4321, randomize_bn=True)
+    for L in network.layer_table("FullyCNNV2")[1:9]:
+        w[L["scope"] + "/kernel"] = w[L["scope"] + "/kernel"] * np.float32(8.0)
+    waves = [noisy_utterance(900 + i, 3000 + 517 * i) for i in range(6)]
+    tc = Enhancer("FullyCNNV2", w, device=0)
+    fp32 = Enhancer("FullyCNNV2", w, device=0, variant="ffma")
+    assert tc.variant == "tc" and fp32.variant == "ffma"
+    tc.host_config(n_streams=2, chunk_rows=60)
+    a = tc.enhance(waves)
+    assert not tc.tc_status()[0] < 65504          # the guard did trip
+    b = fp32.enhance(waves)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    tc.close()
+    fp32.close()
