@@ -565,9 +565,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": total * 4,
                 "api": "rced_enhance_host_async (Enhancer.enhance_host): page-locked host waveforms -> H2D -> K1, K2, K3 -> D2H -> "
-                       "page-locked host output, chunks of ~32768 spectrogram rows over 3 library streams; the steps alternate "
-                       "between two host buffer sets and are queued behind each other, rced_host_sync closes the timed region "
-                       "(host wall clock)"},
+                       "page-locked host output, chunks of ~131072 spectrogram rows through the library's copy-in / compute / "
+                       "copy-out streams; the steps alternate between two host buffer sets and are queued behind each other, "
+                       "rced_host_sync closes the timed region (host wall clock)"},
         "gpu_launches": int(launches),
         "roofline": main_roof,
         # the metric BASELINE.json names for the network kernel: fraction of the FP32 FFMA peak reached by the FP32 kernel

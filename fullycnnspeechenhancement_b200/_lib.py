@@ -48,7 +48,7 @@ SIGNATURES = {
     "rced_enhance_host": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_int, c_p, c_p, c_p]),
     "rced_enhance_host_async": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_int, c_p, c_p, c_p]),
     "rced_host_sync": (ctypes.c_int, [c_p]),
-    "rced_host_config": (ctypes.c_int, [c_p, ctypes.c_int, c_i64]),
+    "rced_host_config": (ctypes.c_int, [c_p, c_i64, c_i64]),
     "rced_mag_phase": (ctypes.c_int, [ctypes.c_int, c_p, c_i64, c_p, c_p, c_p]),
     "rced_sdr_sums": (ctypes.c_int, [ctypes.c_int, c_p, c_p, c_p, c_p, c_p, ctypes.c_int, c_i64, c_p, c_p]),
     "rced_ffma_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),

@@ -3,25 +3,29 @@
 // They replace the body of the reference's batch loop -- parse_audio -> power_spectrum / divide_phase ->
 // sess.run -> rebuild_audio (model_utils/tester.py:104-113, infer.py:54-71) -- for callers that hold their
 // waveforms in HOST memory (numpy arrays): the library owns the device side.  A call is cut into chunks of
-// utterances; chunk i runs on stream i % n_streams as
-//     H2D waveforms -> H2D metadata -> K1 (STFT) -> K2 (network) -> K3 (reconstruction) -> D2H waveforms
-// so that the copies of one chunk overlap the kernels of the others.  Everything the chunks need on the
-// device (waveform in / out, spectrogram workspaces, offset tables) belongs to the handle and only grows;
-// no allocation and no host synchronisation happens in steady state except the back-pressure on the
-// metadata ring (the host may run at most kMetaRing chunks ahead of a stream).
-//
-// Range guard of the tensor-core network kernel: the device-pointer ABI queues the FP32 kernel behind every
-// tensor-core launch (it returns at once unless the guard tripped).  Between the persistent launches of different
-// streams that kernel -- 148 CTAs that need most of an SM's shared memory -- has to wait for whole CTAs of the
-// neighbouring chunk to retire, which holds back the chunk's reconstruction and download.  The host pipeline
-// therefore copies each launch's guard words to page-locked memory instead and looks at them when it
-// synchronises: a chunk whose guard tripped (activations beyond the FP16 range, non-finite input: rare) is
-// recomputed from the caller's buffers with the FP32 kernel before the call returns.
+// utterances that flow through three streams,
+//     copy-in:  H2D waveforms, H2D offset tables
+//     compute:  K1 (STFT) -> K2 (network) -> K3 (reconstruction), chunk after chunk, exactly the sequence of the
+//               device-pointer path
+//     copy-out: D2H guard words, D2H waveforms
+// coupled by events, over a ring of buffer sets (waveform in / out, spectrogram workspaces, offset tables; they
+// belong to the handle and only grow).  The kernels of different chunks never compete for SMs -- a first version
+// that gave every chunk its own stream lost 4 % to small kernels waiting for the persistent network CTAs of the
+// neighbouring chunk to retire -- and the copies of one chunk overlap the kernels of the others.  No allocation
+// and no host synchronisation happens in steady state except the back-pressure of the ring (the host runs at
+// most kSets chunks ahead of the copy-in stream).
 //
 // Caller's buffers: any host memory works (cudaMemcpyAsync); page-locked memory (cudaHostAlloc /
 // cudaHostRegister / torch pin_memory) is what makes the copies asynchronous and the chunks overlap.
+//
+// Range guard of the tensor-core network kernel: the device-pointer ABI queues the FP32 kernel behind every
+// tensor-core launch (it returns at once unless the guard tripped).  The host pipeline copies each launch's guard
+// words to page-locked memory instead and looks at them when it synchronises: a chunk whose guard tripped
+// (activations beyond the FP16 range, non-finite input: rare) is recomputed from the caller's buffers with the FP32
+// kernel before the call returns.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -34,22 +38,20 @@
 
 namespace rced {
 
-constexpr int kMaxStreams = 4;
-constexpr int kMetaRing = 4;   // chunks a stream's metadata staging can hold
-constexpr int kPadGap = 16;    // samples: smaller gaps between consecutive outputs count as padding and may be overwritten
+constexpr int kSets = 4;            // buffer sets in flight
+constexpr int kPadGap = 16;         // samples: smaller gaps between consecutive outputs count as padding and may be overwritten
+constexpr int kPendingMax = 1024;   // chunks whose guard words wait for the next synchronisation
 
-struct StreamCtx {
-    cudaStream_t stream = nullptr;
+struct BufferSet {
     float *d_wav = nullptr, *d_out = nullptr;           // chunk-local waveform in / out
     float *ws_mag = nullptr, *ws_phase = nullptr, *ws_pred = nullptr;
-    unsigned char* d_meta = nullptr;                    // offset tables of the chunk in flight
-    unsigned char* h_meta[kMetaRing] = {};              // pinned staging of the tables
-    cudaEvent_t meta_used[kMetaRing] = {};              // recorded behind the H2D copy that read h_meta[i]
+    unsigned char* d_meta = nullptr;                    // offset tables of the chunk
+    unsigned char* h_meta = nullptr;                    // page-locked staging of the tables
     size_t cap_wav = 0, cap_out = 0, cap_rows = 0, cap_meta = 0;
-    unsigned int uses = 0;
+    cudaEvent_t uploaded = nullptr;    // copy-in:  the set's waveforms and tables are on the device (h_meta may be refilled)
+    cudaEvent_t computed = nullptr;    // compute:  K1-K3 done (d_wav / d_meta may be overwritten, d_out may be downloaded)
+    cudaEvent_t downloaded = nullptr;  // copy-out: d_out has left (the next K3 of this set may write it)
 };
-
-constexpr int kPendingMax = 1024;   // chunks whose guard words wait for the next synchronisation
 
 struct PendingChunk {   // what is needed to recompute a chunk whose range guard tripped
     const float* wav;
@@ -62,13 +64,13 @@ struct PendingChunk {   // what is needed to recompute a chunk whose range guard
 };
 
 struct HostPipe {
-    int n_streams = 3;
     // target spectrogram rows per chunk.  A synchronous call is cut finely (its first upload and last download
-    // overlap nothing, so they should be short); asynchronous calls pipeline behind each other and prefer few,
-    // large chunks (every chunk boundary is a gap in which the small kernels wait for persistent CTAs to retire).
-    int64_t chunk_rows = 49152, chunk_rows_async = 262144;
-    StreamCtx s[kMaxStreams];
-    unsigned int next_stream = 0;   // round robin across calls: consecutive small calls use different streams
+    // overlap nothing, so they should be short); asynchronous calls pipeline behind each other and take larger
+    // chunks (fewer kernel boundaries).
+    int64_t chunk_rows = 32768, chunk_rows_async = 131072;
+    cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    BufferSet set[kSets];
+    unsigned int next_set = 0;
     unsigned int* h_flags = nullptr;   // page-locked [kPendingMax][2]: guard words of the pending tensor-core launches
     std::vector<PendingChunk> pending;
     bool recomputing = false;
@@ -76,37 +78,23 @@ struct HostPipe {
 
 static size_t grow(size_t need) { return need + need / 4 + 256; }
 
-template <class T>
-static cudaError_t ensure(T*& p, size_t& cap, size_t need) {
-    if (need <= cap) return cudaSuccess;
-    if (p) {
-        cudaError_t e = cudaFree(p);   // (synchronises the device: only while the buffers still grow)
-        if (e != cudaSuccess) return e;
-        p = nullptr;
-        cap = 0;
-    }
-    const size_t n = grow(need);
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-    if (e == cudaSuccess) cap = n;
-    return e;
-}
-
 void host_pipe_destroy(HostPipe* p) {
     if (!p) return;
-    for (StreamCtx& c : p->s) {
-        if (c.stream) cudaStreamSynchronize(c.stream);
-        cudaFree(c.d_wav);
-        cudaFree(c.d_out);
-        cudaFree(c.ws_mag);
-        cudaFree(c.ws_phase);
-        cudaFree(c.ws_pred);
-        cudaFree(c.d_meta);
-        for (int i = 0; i < kMetaRing; ++i) {
-            if (c.h_meta[i]) cudaFreeHost(c.h_meta[i]);
-            if (c.meta_used[i]) cudaEventDestroy(c.meta_used[i]);
-        }
-        if (c.stream) cudaStreamDestroy(c.stream);
+    for (cudaStream_t s : {p->s_in, p->s_compute, p->s_out})
+        if (s) cudaStreamSynchronize(s);
+    for (BufferSet& b : p->set) {
+        cudaFree(b.d_wav);
+        cudaFree(b.d_out);
+        cudaFree(b.ws_mag);
+        cudaFree(b.ws_phase);
+        cudaFree(b.ws_pred);
+        cudaFree(b.d_meta);
+        if (b.h_meta) cudaFreeHost(b.h_meta);
+        for (cudaEvent_t e : {b.uploaded, b.computed, b.downloaded})
+            if (e) cudaEventDestroy(e);
     }
+    for (cudaStream_t s : {p->s_in, p->s_compute, p->s_out})
+        if (s) cudaStreamDestroy(s);
     if (p->h_flags) cudaFreeHost(p->h_flags);
     delete p;
 }
@@ -114,18 +102,16 @@ void host_pipe_destroy(HostPipe* p) {
 static int pipe_get(rced_handle* h, HostPipe** out) {
     if (!h->pipe) {
         HostPipe* p = new HostPipe();
-        for (int i = 0; i < kMaxStreams; ++i) {
-            cudaError_t e = cudaStreamCreateWithFlags(&p->s[i].stream, cudaStreamNonBlocking);
-            for (int j = 0; j < kMetaRing && e == cudaSuccess; ++j) e = cudaEventCreateWithFlags(&p->s[i].meta_used[j], cudaEventDisableTiming);
-            if (e != cudaSuccess) {
-                host_pipe_destroy(p);
-                return cuda_fail(e, "host pipeline: stream / event creation");
-            }
-        }
-        cudaError_t e = cudaHostAlloc(&p->h_flags, sizeof(unsigned int) * 2 * kPendingMax, cudaHostAllocDefault);
+        cudaError_t e = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking);
+        for (BufferSet& b : p->set)
+            for (cudaEvent_t* ev : {&b.uploaded, &b.computed, &b.downloaded})
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaHostAlloc(&p->h_flags, sizeof(unsigned int) * 2 * kPendingMax, cudaHostAllocDefault);
         if (e != cudaSuccess) {
             host_pipe_destroy(p);
-            return cuda_fail(e, "host pipeline: pinned guard words");
+            return cuda_fail(e, "host pipeline: streams / events / pinned guard words");
         }
         p->pending.reserve(kPendingMax);
         h->pipe = p;
@@ -136,9 +122,23 @@ static int pipe_get(rced_handle* h, HostPipe** out) {
 
 static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// one chunk [c0, c1) of the call on stream context c
-static int run_chunk(rced_handle* h, StreamCtx& c, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int c0, int c1,
-                     int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len) {
+// (Re)allocation of a set's buffers.  cudaFree synchronises the device, so queued work that uses the old buffers
+// has finished; it only happens while the buffers still grow.
+template <class T>
+static cudaError_t ensure(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return cudaSuccess;
+    cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t n = grow(need);
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+}
+
+// one chunk [c0, c1) of the call through buffer set b
+static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* wav, const int64_t* wav_off, const int32_t* wav_len,
+                     int c0, int c1, int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len) {
     const int n = c1 - c0;
     // sample ranges of the chunk in the caller's buffers, frame counts
     int64_t in_lo = INT64_MAX, in_hi = 0, o_lo = INT64_MAX, o_hi = 0, rows = 0, max_rows = 0;
@@ -161,41 +161,38 @@ static int run_chunk(rced_handle* h, StreamCtx& c, const float* wav, const int64
     const size_t meta_bytes = align16(o_out_len + 4 * (size_t)n);
 
     cudaError_t e;
-    if ((e = ensure(c.d_wav, c.cap_wav, (size_t)(in_hi - in_lo))) != cudaSuccess) return cuda_fail(e, "host pipeline: waveform buffer");
-    if ((e = ensure(c.d_out, c.cap_out, (size_t)(o_hi - o_lo))) != cudaSuccess) return cuda_fail(e, "host pipeline: output buffer");
-    if ((size_t)rows > c.cap_rows) {
-        cudaFree(c.ws_mag);     // (cudaFree synchronises the device: queued work that uses the old buffers has finished)
-        cudaFree(c.ws_phase);
-        cudaFree(c.ws_pred);
-        c.ws_mag = c.ws_phase = c.ws_pred = nullptr;
-        c.cap_rows = 0;
+    // the host may refill this set's table staging once its previous upload has run (back-pressure: the host is at
+    // most kSets chunks ahead of the copy-in stream)
+    if ((e = cudaEventSynchronize(b.uploaded)) != cudaSuccess) return cuda_fail(e, "host pipeline: table staging");
+    if ((e = ensure(b.d_wav, b.cap_wav, (size_t)(in_hi - in_lo))) != cudaSuccess) return cuda_fail(e, "host pipeline: waveform buffer");
+    if ((e = ensure(b.d_out, b.cap_out, (size_t)(o_hi - o_lo))) != cudaSuccess) return cuda_fail(e, "host pipeline: output buffer");
+    if ((size_t)rows > b.cap_rows) {
+        cudaFree(b.ws_mag);
+        cudaFree(b.ws_phase);
+        cudaFree(b.ws_pred);
+        b.ws_mag = b.ws_phase = b.ws_pred = nullptr;
+        b.cap_rows = 0;
         const size_t nr = grow((size_t)rows);
-        if ((e = cudaMalloc(&c.ws_mag, nr * RCED_FREQ_BINS * sizeof(float))) != cudaSuccess ||
-            (e = cudaMalloc(&c.ws_phase, nr * RCED_FREQ_BINS * 2 * sizeof(float))) != cudaSuccess ||
-            (e = cudaMalloc(&c.ws_pred, nr * RCED_FREQ_BINS * sizeof(float))) != cudaSuccess)
+        if ((e = cudaMalloc(&b.ws_mag, nr * RCED_FREQ_BINS * sizeof(float))) != cudaSuccess ||
+            (e = cudaMalloc(&b.ws_phase, nr * RCED_FREQ_BINS * 2 * sizeof(float))) != cudaSuccess ||
+            (e = cudaMalloc(&b.ws_pred, nr * RCED_FREQ_BINS * sizeof(float))) != cudaSuccess)
             return cuda_fail(e, "host pipeline: spectrogram workspaces");
-        c.cap_rows = nr;
+        b.cap_rows = nr;
     }
-    if (meta_bytes > c.cap_meta) {
-        cudaStreamSynchronize(c.stream);   // the old tables may still be read by queued work
-        const size_t nb = (grow(meta_bytes) + 255) & ~(size_t)255;   // every ring slot starts 256-byte aligned
-        cudaFree(c.d_meta);
-        c.d_meta = nullptr;
-        for (int i = 0; i < kMetaRing; ++i) {
-            if (c.h_meta[i]) cudaFreeHost(c.h_meta[i]);
-            c.h_meta[i] = nullptr;
-        }
-        c.cap_meta = 0;
-        if ((e = cudaMalloc(&c.d_meta, nb * kMetaRing)) != cudaSuccess) return cuda_fail(e, "host pipeline: table buffer");
-        for (int i = 0; i < kMetaRing; ++i)
-            if ((e = cudaHostAlloc(&c.h_meta[i], nb, cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "host pipeline: pinned table staging");
-        c.cap_meta = nb;
+    if (meta_bytes > b.cap_meta) {
+        cudaDeviceSynchronize();   // the old tables may still be read by queued work
+        const size_t nb = (grow(meta_bytes) + 255) & ~(size_t)255;
+        cudaFree(b.d_meta);
+        if (b.h_meta) cudaFreeHost(b.h_meta);
+        b.d_meta = nullptr;
+        b.h_meta = nullptr;
+        b.cap_meta = 0;
+        if ((e = cudaMalloc(&b.d_meta, nb)) != cudaSuccess) return cuda_fail(e, "host pipeline: table buffer");
+        if ((e = cudaHostAlloc(&b.h_meta, nb, cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "host pipeline: pinned table staging");
+        b.cap_meta = nb;
     }
-    const int slot = (int)(c.uses++ % kMetaRing);
-    // back-pressure: the copy that read this staging slot kMetaRing chunks ago has run
-    if ((e = cudaEventSynchronize(c.meta_used[slot])) != cudaSuccess) return cuda_fail(e, "host pipeline: table staging");
-    unsigned char* hm = c.h_meta[slot];
-    unsigned char* dm = c.d_meta + (size_t)slot * c.cap_meta;
+    unsigned char* hm = b.h_meta;
+    unsigned char* dm = b.d_meta;
     int64_t* m_wav_off = reinterpret_cast<int64_t*>(hm + o_wav_off);
     int64_t* m_row_off = reinterpret_cast<int64_t*>(hm + o_row_off);
     int64_t* m_out_off = reinterpret_cast<int64_t*>(hm + o_out_off);
@@ -213,63 +210,57 @@ static int run_chunk(rced_handle* h, StreamCtx& c, const float* wav, const int64
     }
     m_row_off[n] = r;
 
-    if ((e = cudaMemcpyAsync(c.d_wav, wav + in_lo, (size_t)(in_hi - in_lo) * sizeof(float), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess)
+    // ---- copy-in: behind the kernels that read this set's previous waveforms and tables
+    // development aid (tools/e2e_sweep.py): RCED_HOST_NOCOPY=1 leaves the waveform copies out to see what they cost
+    static const bool no_copy = getenv("RCED_HOST_NOCOPY") != nullptr;
+    cudaStreamWaitEvent(pipe->s_in, b.computed, 0);
+    if (!no_copy &&
+        (e = cudaMemcpyAsync(b.d_wav, wav + in_lo, (size_t)(in_hi - in_lo) * sizeof(float), cudaMemcpyHostToDevice, pipe->s_in)) != cudaSuccess)
         return cuda_fail(e, "host pipeline: H2D waveforms");
-    if ((e = cudaMemcpyAsync(dm, hm, meta_bytes, cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return cuda_fail(e, "host pipeline: H2D tables");
-    cudaEventRecord(c.meta_used[slot], c.stream);
+    if ((e = cudaMemcpyAsync(dm, hm, meta_bytes, cudaMemcpyHostToDevice, pipe->s_in)) != cudaSuccess) return cuda_fail(e, "host pipeline: H2D tables");
+    cudaEventRecord(b.uploaded, pipe->s_in);
+
+    // ---- compute: behind the upload, and behind the download of what this set's d_out held before
     const int64_t* d_wav_off = reinterpret_cast<const int64_t*>(dm + o_wav_off);
     const int64_t* d_row_off = reinterpret_cast<const int64_t*>(dm + o_row_off);
     const int64_t* d_out_off = reinterpret_cast<const int64_t*>(dm + o_out_off);
     const int32_t* d_wav_len = reinterpret_cast<const int32_t*>(dm + o_wav_len);
     const int32_t* d_out_len = reinterpret_cast<const int32_t*>(dm + o_out_len);
-    int rc = rced_stft(h, c.d_wav, d_wav_off, d_wav_len, d_row_off, n, rows, c.ws_mag, c.ws_phase, c.stream);
+    cudaStreamWaitEvent(pipe->s_compute, b.uploaded, 0);
+    cudaStreamWaitEvent(pipe->s_compute, b.downloaded, 0);
+    int rc = rced_stft(h, b.d_wav, d_wav_off, d_wav_len, d_row_off, n, rows, b.ws_mag, b.ws_phase, pipe->s_compute);
     if (rc != RCED_OK) return rc;
-    HostPipe* pipe = h->pipe;
     unsigned int* d_flags = nullptr;
-    rc = forward_impl(h, c.ws_mag, d_row_off, n, rows, c.ws_pred, c.stream, pipe->recomputing ? nullptr : &d_flags);
+    rc = forward_impl(h, b.ws_mag, d_row_off, n, rows, b.ws_pred, pipe->s_compute, pipe->recomputing ? nullptr : &d_flags);
     if (rc != RCED_OK) return rc;
-    if (d_flags) {   // tensor-core launch: its guard words travel to the host behind it, the chunk is remembered
-        e = cudaMemcpyAsync(pipe->h_flags + 2 * pipe->pending.size(), d_flags, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream);
+    rc = rced_istft(h, b.ws_pred, b.ws_phase, d_row_off, n, max_rows, irfft_n, b.d_out, d_out_off, d_out_len, pipe->s_compute);
+    if (rc != RCED_OK) return rc;
+    cudaEventRecord(b.computed, pipe->s_compute);
+
+    // ---- copy-out
+    cudaStreamWaitEvent(pipe->s_out, b.computed, 0);
+    if (d_flags) {   // tensor-core launch: its guard words travel to the host, the chunk is remembered
+        e = cudaMemcpyAsync(pipe->h_flags + 2 * pipe->pending.size(), d_flags, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, pipe->s_out);
         if (e != cudaSuccess) return cuda_fail(e, "host pipeline: D2H guard words");
         pipe->pending.push_back(PendingChunk{wav, wav_off, wav_len, c0, c1, irfft_n, out, out_off, out_len});
     }
-    rc = rced_istft(h, c.ws_pred, c.ws_phase, d_row_off, n, max_rows, irfft_n, c.d_out, d_out_off, d_out_len, c.stream);
-    if (rc != RCED_OK) return rc;
-    if (out_contiguous) {
-        e = cudaMemcpyAsync(out + o_lo, c.d_out, (size_t)(o_hi - o_lo) * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    e = cudaSuccess;
+    if (no_copy) {
+    } else if (out_contiguous) {
+        e = cudaMemcpyAsync(out + o_lo, b.d_out, (size_t)(o_hi - o_lo) * sizeof(float), cudaMemcpyDeviceToHost, pipe->s_out);
     } else {   // gaps between the outputs belong to the caller: copy utterance by utterance
-        e = cudaSuccess;
         for (int u = c0; u < c1 && e == cudaSuccess; ++u)
-            e = cudaMemcpyAsync(out + out_off[u], c.d_out + (out_off[u] - o_lo), (size_t)out_len[u] * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+            e = cudaMemcpyAsync(out + out_off[u], b.d_out + (out_off[u] - o_lo), (size_t)out_len[u] * sizeof(float), cudaMemcpyDeviceToHost, pipe->s_out);
     }
+    cudaEventRecord(b.downloaded, pipe->s_out);
     return e == cudaSuccess ? RCED_OK : cuda_fail(e, "host pipeline: D2H waveforms");
-}
-
-}  // namespace rced
-
-using namespace rced;
-
-extern "C" {
-
-int rced_host_config(rced_handle* h, int n_streams, int64_t chunk_rows) {
-    if (!h) return fail(RCED_ERR_ARG, "null handle");
-    if (n_streams < 1 || n_streams > kMaxStreams) return fail(RCED_ERR_ARG, "n_streams must be 1.." + std::to_string(kMaxStreams));
-    if (chunk_rows < 1) return fail(RCED_ERR_ARG, "chunk_rows must be positive");
-    DeviceGuard guard(h->device);
-    HostPipe* p = nullptr;
-    const int rc = pipe_get(h, &p);
-    if (rc != RCED_OK) return rc;
-    p->n_streams = n_streams;
-    p->chunk_rows = chunk_rows;
-    p->chunk_rows_async = chunk_rows;
-    return RCED_OK;
 }
 
 static int host_sync_impl(rced_handle* h) {
     HostPipe* p = h->pipe;
     if (!p) return RCED_OK;
-    for (int i = 0; i < kMaxStreams; ++i) {
-        cudaError_t e = cudaStreamSynchronize(p->s[i].stream);
+    for (cudaStream_t s : {p->s_in, p->s_compute, p->s_out}) {
+        cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return cuda_fail(e, "rced_host_sync");
     }
     // range guard of the tensor-core launches since the last synchronisation (see the head of this file)
@@ -283,11 +274,11 @@ static int host_sync_impl(rced_handle* h) {
         const int variant = h->variant;
         h->variant = RCED_VARIANT_FFMA;
         p->recomputing = true;
-        rc = run_chunk(h, p->s[0], q.wav, q.wav_off, q.wav_len, q.c0, q.c1, q.irfft_n, q.out, q.out_off, q.out_len);
+        rc = run_chunk(h, p, p->set[0], q.wav, q.wav_off, q.wav_len, q.c0, q.c1, q.irfft_n, q.out, q.out_off, q.out_len);
         p->recomputing = false;
         h->variant = variant;
         if (rc == RCED_OK) {
-            cudaError_t e = cudaStreamSynchronize(p->s[0].stream);
+            cudaError_t e = cudaStreamSynchronize(p->s_out);
             if (e != cudaSuccess) rc = cuda_fail(e, "rced_host_sync (FP32 recomputation)");
         }
     }
@@ -311,7 +302,7 @@ static int enhance_host_impl(rced_handle* h, const float* wav, const int64_t* wa
     HostPipe* p = nullptr;
     int rc = pipe_get(h, &p);
     if (rc != RCED_OK) return rc;
-    // chunks of about `target_rows` spectrogram rows; the first and the last chunk of a long synchronous call are a
+    // chunks of about `chunk_rows` spectrogram rows; the first and the last chunk of a long synchronous call are a
     // quarter of that: nothing overlaps the first upload and the last download
     const int64_t chunk_rows = async ? p->chunk_rows_async : p->chunk_rows;
     std::vector<int> bounds;
@@ -335,10 +326,28 @@ static int enhance_host_impl(rced_handle* h, const float* wav, const int64_t* wa
             rc = host_sync_impl(h);
             if (rc != RCED_OK) return rc;
         }
-        StreamCtx& c = p->s[p->next_stream++ % (unsigned int)p->n_streams];
-        rc = run_chunk(h, c, wav, wav_off, wav_len, bounds[i], bounds[i + 1], irfft_n, out, out_off, out_len);
+        BufferSet& b = p->set[p->next_set++ % (unsigned int)kSets];
+        rc = run_chunk(h, p, b, wav, wav_off, wav_len, bounds[i], bounds[i + 1], irfft_n, out, out_off, out_len);
         if (rc != RCED_OK) return rc;
     }
+    return RCED_OK;
+}
+
+}  // namespace rced
+
+using namespace rced;
+
+extern "C" {
+
+int rced_host_config(rced_handle* h, int64_t chunk_rows, int64_t chunk_rows_async) {
+    if (!h) return fail(RCED_ERR_ARG, "null handle");
+    if (chunk_rows < 1 || chunk_rows_async < 1) return fail(RCED_ERR_ARG, "chunk sizes must be positive");
+    DeviceGuard guard(h->device);
+    HostPipe* p = nullptr;
+    const int rc = pipe_get(h, &p);
+    if (rc != RCED_OK) return rc;
+    p->chunk_rows = chunk_rows;
+    p->chunk_rows_async = chunk_rows_async;
     return RCED_OK;
 }
 

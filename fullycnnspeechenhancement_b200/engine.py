@@ -6,9 +6,9 @@ the C ABI of librced_b200.so.  PyTorch is used only as the buffer / stream inter
 (``torch.empty``, ``data_ptr()``, pinned host memory, CUDA streams); it performs no arithmetic
 on the path.  There is no CPU fallback: constructing an Enhancer without a CUDA device raises.
 
-Utterances are independent, so a batch is split into chunks that are
-pipelined over a few CUDA streams (H2D copy, K1-K3, D2H copy overlap), and across GPUs by
-``partition_utterances`` with no collective.
+Utterances are independent, so a batch is split into chunks that the
+library pipelines over its copy-in / compute / copy-out streams (rced_enhance_host), and across
+GPUs by ``partition_utterances`` with no collective.
 """
 import ctypes
 
@@ -49,6 +49,28 @@ def partition_utterances(lengths, world_size):
         parts[r].append(int(i))
         load[r] += frames[i]
     return [np.array(sorted(p), dtype=np.int64) for p in parts]
+
+
+def host_tables(lengths, out_lens=None, align=4):
+    """Offset tables of a packed batch in HOST memory for rced_enhance_host: utterance u occupies
+    ``wav[wav_off[u] : wav_off[u] + wav_len[u]]`` (starts aligned to ``align`` samples so that the STFT kernel can
+    use its 8-byte loads) and its result goes to the same offset of the output buffer, ``out_len[u]`` samples --
+    default: the input length; the reference truncates what it rebuilds, (T+1)*128 samples, to
+    ``len(clean_sig[u])`` (model_utils/tester.py:107-113, model_utils/utils.py:181-182)."""
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    if lengths.ndim != 1 or len(lengths) == 0:
+        raise ValueError("lengths must be a non-empty 1-D array")
+    if np.any(lengths < 1):
+        raise ValueError("every utterance needs at least one sample (the reference raises IndexError on L=0)")
+    rebuilt = (num_frames(lengths) + 1) * FRAME_HOP
+    ol = lengths if out_lens is None else np.asarray(out_lens, dtype=np.int64)
+    if ol.shape != lengths.shape or np.any(ol < 0):
+        raise ValueError("out_lens must hold one non-negative length per utterance")
+    ol = np.minimum(ol, rebuilt)          # numpy slicing [:L] never extends (utils.py:181-182)
+    span = (np.maximum(lengths, ol) + align - 1) // align * align
+    off = np.concatenate([[0], np.cumsum(span)[:-1]]).astype(np.int64)
+    return {"n": len(lengths), "lengths": lengths, "wav_off": off, "wav_len": lengths.astype(np.int32),
+            "out_off": off, "out_len": ol.astype(np.int32), "total": int(span.sum())}
 
 
 def _ptr(t):
@@ -232,55 +254,13 @@ class Enhancer(object):
                                 stream=stream)
         return d_out
 
-    def run_plan_host(self, plan, h_wav, h_out, d_wav, d_out, n_streams=3):
-        """End-to-end: pinned host waveform -> H2D -> K1-K3 -> D2H -> pinned host output, chunks
-        pipelined over `n_streams` CUDA streams.  Returns after everything has completed."""
-        if self._streams is None or len(self._streams) < n_streams:
-            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
-        cur = torch.cuda.current_stream(self.device)
-        for s in self._streams[:n_streams]:
-            s.wait_stream(cur)
-        off = plan["wav_off_host"]
-        lens = plan["lengths"]
-        for ci, (c0, c1, rows, max_rows, ro_pos) in enumerate(plan["chunks"]):
-            k = ci % n_streams
-            s = self._streams[k]
-            ws_mag, ws_phase, ws_pred = self._workspace(k, plan["max_chunk_rows"])
-            a, b = int(off[c0]), int(off[c1 - 1] + lens[c1 - 1])
-            row_off = plan["row_off_all"][ro_pos:ro_pos + (c1 - c0) + 1]
-            with torch.cuda.stream(s):
-                d_wav[a:b].copy_(h_wav[a:b], non_blocking=True)
-                self.enhance_device(d_wav, plan["wav_off"][c0:c1], plan["wav_len"][c0:c1], row_off, rows, max_rows,
-                                    d_out, plan["wav_off"][c0:c1], plan["wav_len"][c0:c1], ws_mag, ws_phase, ws_pred,
-                                    stream=s)
-                h_out[a:b].copy_(d_out[a:b], non_blocking=True)
-        for s in self._streams[:n_streams]:
-            cur.wait_stream(s)
-        cur.synchronize()
-        return h_out
-
     # ------------------------------------------------------------------ host-buffer API (C side owns the device)
     def host_tables(self, lengths, out_lens=None, align=4):
-        """Offset tables of a packed batch in HOST memory for ``enhance_host``: utterance u occupies
-        ``wav[wav_off[u] : wav_off[u] + wav_len[u]]`` (starts aligned to ``align`` samples so that the STFT
-        kernel can use its vectorised loads) and its result goes to the same offset of the output buffer,
-        ``out_len[u]`` samples (default: the input length; the reference truncates to ``len(clean_sig[u])``,
-        model_utils/utils.py:181-182, at most the (T+1)*128 samples it rebuilds).  Cached for repeated shapes."""
-        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
-        if lengths.ndim != 1 or len(lengths) == 0:
-            raise ValueError("lengths must be a non-empty 1-D array")
-        if np.any(lengths < 1):
-            raise ValueError("every utterance needs at least one sample (the reference raises IndexError on L=0)")
-        key = (lengths.tobytes(), None if out_lens is None else np.asarray(out_lens, np.int64).tobytes(), align)
+        """``host_tables`` of this module, cached for repeated shapes (streaming blocks, fixed batch shapes)."""
+        key = (np.asarray(lengths, np.int64).tobytes(), None if out_lens is None else np.asarray(out_lens, np.int64).tobytes(), align)
         t = self._tables.get(key)
         if t is None:
-            rebuilt = (num_frames(lengths) + 1) * FRAME_HOP
-            ol = lengths if out_lens is None else np.asarray(out_lens, dtype=np.int64)
-            ol = np.minimum(ol, rebuilt)          # numpy slicing [:L] never extends (utils.py:181-182)
-            span = (np.maximum(lengths, ol) + align - 1) // align * align
-            off = np.concatenate([[0], np.cumsum(span)[:-1]]).astype(np.int64)
-            t = {"n": len(lengths), "lengths": lengths, "wav_off": off, "wav_len": lengths.astype(np.int32),
-                 "out_off": off, "out_len": ol.astype(np.int32), "total": int(span.sum())}
+            t = host_tables(lengths, out_lens, align)
             if len(self._tables) >= 16:
                 self._tables.pop(next(iter(self._tables)))
             self._tables[key] = t
@@ -303,8 +283,9 @@ class Enhancer(object):
     def host_sync(self):
         _lib.check(self.lib.rced_host_sync(self._h))
 
-    def host_config(self, n_streams=3, chunk_rows=32768):
-        _lib.check(self.lib.rced_host_config(self._h, int(n_streams), int(chunk_rows)))
+    def host_config(self, chunk_rows=32768, chunk_rows_async=None):
+        """Target spectrogram rows per chunk of the host pipeline, for synchronous and for asynchronous calls."""
+        _lib.check(self.lib.rced_host_config(self._h, int(chunk_rows), int(chunk_rows_async or chunk_rows)))
 
     def _stage(self, total):
         """Persistent page-locked staging (input, output), grown geometrically: enhance() never pins per call."""

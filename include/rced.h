@@ -188,9 +188,10 @@ int rced_enhance(rced_handle* h, const float* wav, const int64_t* wav_off, const
 /* The batch loop of the reference with HOST waveforms in and out: replaces
  * parse_audio -> power_spectrum / divide_phase -> sess.run(pred) -> rebuild_audio
  * (model_utils/tester.py:104-113, infer.py:54-71) for callers that hold numpy arrays.  The library owns
- * the device side: the call is cut into chunks of utterances that are pipelined over a few internal
- * streams (H2D, K1, K2, K3, D2H of different chunks overlap); device buffers belong to the handle and
- * only grow.
+ * the device side: the call is cut into chunks of utterances that flow through a copy-in, a compute and
+ * a copy-out stream over a ring of buffer sets (the copies of one chunk overlap the kernels of the
+ * others; the kernels run in the order of the device-pointer path); device buffers belong to the
+ * handle and only grow.
  *   wav      HOST float32, utterances concatenated (gaps allowed); page-locked memory makes the
  *            copies asynchronous (pageable memory works, without overlap)
  *   wav_off  HOST int64[n_utt] first sample of utterance u;  wav_len HOST int32[n_utt] (>= 1)
@@ -204,15 +205,15 @@ int rced_enhance(rced_handle* h, const float* wav, const int64_t* wav_off, const
  * rced_host_sync(h); consecutive async calls pipeline behind each other.  With the tensor-core
  * variant the range guard is evaluated at the synchronisation: a chunk whose guard tripped is
  * recomputed with the FP32 kernel before rced_host_sync / rced_enhance_host returns.
- * rced_host_config: number of internal streams (1..4, default 3) and target spectrogram rows per
- * chunk (defaults: 49152 for the synchronous call, whose first and last chunk are a quarter of that,
- * 262144 for asynchronous calls). */
+ * rced_host_config: target spectrogram rows per chunk for the synchronous call (default 32768; the
+ * first and the last chunk of a long call are a quarter of that, because nothing overlaps the first
+ * upload and the last download) and for asynchronous calls (default 131072). */
 int rced_enhance_host(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt,
                       int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len);
 int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt,
                             int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len);
 int rced_host_sync(rced_handle* h);
-int rced_host_config(rced_handle* h, int n_streams, int64_t chunk_rows);
+int rced_host_config(rced_handle* h, int64_t chunk_rows, int64_t chunk_rows_async);
 
 /* Element-wise |X| and X/|X| of `n` complex64 values (X == 0 -> phase 1+0j).  Replaces
  * AudioFeature.power_spectrum / divide_phase (data_utils/audio_feature.py:101-115) when the

@@ -390,3 +390,24 @@ def test_entry_point_helpers_on_the_cpu(tmp_path):
     assert mag.shape == (1, 7, 129, 1) and ph.shape == (1, 7, 129)
     assert np.array_equal(mag.reshape(-1), np.abs(spec).reshape(-1))            # memory order kept: a reshape, no transpose
     assert np.allclose(ph.reshape(129, 7) * np.abs(spec), spec)
+
+
+def test_host_tables_follow_the_reference_truncation():
+    """Offset tables of rced_enhance_host: aligned starts, outputs truncated like rebuild_audio does -- the reference rebuilds
+    (T+1)*128 samples and slices them to len(clean_sig[i]) (model_utils/tester.py:107-113, utils.py:181-182), so an
+    output can be LONGER than the noisy input but never longer than what was rebuilt."""
+    from fullycnnspeechenhancement_b200.engine import host_tables, num_frames
+    lens = np.array([1, 255, 256, 257, 1000, 32000, 4321])
+    t = host_tables(lens)
+    assert np.all(t["wav_off"] % 4 == 0) and np.array_equal(t["wav_len"], lens) and np.array_equal(t["out_len"], lens)
+    assert np.all(t["wav_off"][1:] >= t["wav_off"][:-1] + lens[:-1]) and t["total"] >= t["wav_off"][-1] + lens[-1]
+    rebuilt = (num_frames(lens) + 1) * 128
+    want = np.array([5000, 100, 256, 300, 1100, 31000, 4400])          # len(clean) per utterance
+    t2 = host_tables(lens, out_lens=want)
+    assert np.array_equal(t2["out_len"], np.minimum(want, rebuilt))
+    assert t2["out_len"][4] == 1100 > lens[4]                            # longer than the input, still inside (T+1)*128 = 1152
+    assert np.all(t2["wav_off"][1:] >= t2["out_off"][:-1] + t2["out_len"][:-1])   # outputs never overlap the next utterance
+    with pytest.raises(ValueError):
+        host_tables(np.array([10, 0]))
+    with pytest.raises(ValueError):
+        host_tables(np.array([10, 20]), out_lens=[5])
