@@ -392,13 +392,18 @@ def main():
     total = int(lengths.sum())
     # two sets of page-locked host buffers: step i + 1 is queued while step i still runs (a consumer would read the
     # other set meanwhile)
-    h_wav = [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(2)]
-    h_out = [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(2)]
-    hv = h_wav[0].numpy()
+    # (library-allocated page-locked memory; RCED_BENCH_WC=1: write-combined input buffers, an experiment)
+    from fullycnnspeechenhancement_b200.engine import PinnedArray
+    wc = os.environ.get("RCED_BENCH_WC") == "1"
+    pins = [PinnedArray(total, write_combined=wc) for _ in range(2)] + [PinnedArray(total) for _ in range(2)]
+    h_wav = [pins[0].array, pins[1].array]
+    h_out = [pins[2].array, pins[3].array]
+    staged = np.empty(total, np.float32)
     for i in range(N_UTT):
-        hv[i * UTT_SAMPLES:(i + 1) * UTT_SAMPLES] = pool[(i + rank) % POOL]
-    h_wav[1].copy_(h_wav[0])
-    d_wav = h_wav[0].to(dev)
+        staged[i * UTT_SAMPLES:(i + 1) * UTT_SAMPLES] = pool[(i + rank) % POOL]
+    h_wav[0][:] = staged
+    h_wav[1][:] = staged
+    d_wav = torch.from_numpy(staged).to(dev)
     d_out = torch.empty_like(d_wav)
 
     T = int(num_frames(UTT_SAMPLES))
@@ -435,6 +440,25 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def per_rank(x):
+        """[x of rank 0, x of rank 1, ...] on every rank (diagnostics of the host side: which ranks are slow)."""
+        if world == 1:
+            return [float(x)]
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def gpu_numa_node():
+        try:
+            bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+            dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+            devid = torch.cuda.get_device_properties(local_rank).pci_device_id
+            with open("/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, devid)) as f:
+                return int(f.read().strip())
+        except Exception:
+            return -99
 
     def timed_device_steps(n_steps, n_warm):
         """n_steps passes of K1 -> K2 -> K3 with CUDA events around every kernel; returns (ms total, [K1, K2, K3] mean ms)."""
@@ -495,6 +519,8 @@ def main():
     wall = time.perf_counter() - t0
     f1.record()
     barrier()
+    e2e_rank_ms = per_rank(wall * 1e3 / args.steps)
+    numa_nodes = per_rank(gpu_numa_node())
     e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), wall * 1e3))
     e2e_value = world * audio_s_per_step * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
@@ -564,6 +590,8 @@ def main():
                    "skip_storage": "global scratch (L2), one region per resident CTA" if args.variant == "tc" else "tensor memory"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": total * 4,
+                "ms_per_step_by_rank": e2e_rank_ms, "gpu_numa_node_by_rank": [int(x) for x in numa_nodes],
+                "host_cores": host_cores(),
                 "api": "rced_enhance_host_async (Enhancer.enhance_host): page-locked host waveforms -> H2D -> K1, K2, K3 -> D2H -> "
                        "page-locked host output, chunks of ~131072 spectrogram rows through the library's copy-in / compute / "
                        "copy-out streams; the steps alternate between two host buffer sets and are queued behind each other, "

@@ -351,6 +351,19 @@ int rced_host_config(rced_handle* h, int64_t chunk_rows, int64_t chunk_rows_asyn
     return RCED_OK;
 }
 
+int rced_host_alloc(size_t bytes, int write_combined, void** out) {
+    if (!out || bytes == 0) return fail(RCED_ERR_ARG, "bad argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_host_alloc");
+}
+
+int rced_host_free(void* p) {
+    if (!p) return RCED_OK;
+    cudaError_t e = cudaFreeHost(p);
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_host_free");
+}
+
 int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav_off, const int32_t* wav_len, int n_utt, int irfft_n,
                             float* out, const int64_t* out_off, const int32_t* out_len) {
     return enhance_host_impl(h, wav, wav_off, wav_len, n_utt, irfft_n, out, out_off, out_len, true);

@@ -73,6 +73,30 @@ def host_tables(lengths, out_lens=None, align=4):
             "out_off": off, "out_len": ol.astype(np.int32), "total": int(span.sum())}
 
 
+class PinnedArray(object):
+    """float32 numpy array in page-locked host memory from the library (rced_host_alloc): what rced_enhance_host wants
+    for asynchronous copies, without torch.  ``write_combined=True`` is for input buffers the host only writes."""
+
+    def __init__(self, n, write_combined=False):
+        self._lib = _lib.lib()
+        p = ctypes.c_void_p()
+        _lib.check(self._lib.rced_host_alloc(int(n) * 4, 1 if write_combined else 0, ctypes.byref(p)))
+        self._p = p
+        self.array = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(int(n),))
+
+    def close(self):
+        if self._p is not None:
+            self.array = None
+            self._lib.rced_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 

@@ -215,6 +215,12 @@ int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav
 int rced_host_sync(rced_handle* h);
 int rced_host_config(rced_handle* h, int64_t chunk_rows, int64_t chunk_rows_async);
 
+/* Page-locked host memory for the buffers above (cudaHostAlloc), for callers that have no other way to pin memory.
+ * write_combined != 0: write-combined memory -- faster for the device to read, very slow for the CPU to read: for
+ * INPUT buffers the host only writes. */
+int rced_host_alloc(size_t bytes, int write_combined, void** out);
+int rced_host_free(void* p);
+
 /* Element-wise |X| and X/|X| of `n` complex64 values (X == 0 -> phase 1+0j).  Replaces
  * AudioFeature.power_spectrum / divide_phase (data_utils/audio_feature.py:101-115) when the
  * caller already holds a complex spectrogram (model_utils/tester.py:104-105, infer.py:57-60).
