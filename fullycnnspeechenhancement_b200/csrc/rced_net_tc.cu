@@ -634,10 +634,31 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
 // sum from the warp that owns its 32-row block (outp[0]) and one from the next block (outp[1]).
 // E rows that belong to no frame of the parity, and diagonals that leave the frame, only ever
 // reach rows of the other parity or halo rows, which are not stored.
+// Batch boundary (RCED_TC_BOUNDARY, default 1): the epilogue of the output layer's row tile t also stages the NEXT
+// batch's first-layer input for the rows of tile t -- an in-place update of plane 0 like every conv epilogue (it
+// therefore waits for the commits of tiles t-1, t, t+1: their MMAs read tile t's rows) -- so that the boundary
+// between two batches is an ordinary layer boundary: the next batch's first layer starts on the early row tiles
+// while the output layer still runs on the late ones.  (0: the round-1 form -- all rows staged between a group's
+// two output-layer tiles, behind final_done, the first layer behind in_ready of all sixteen warps.)
+#ifndef RCED_TC_BOUNDARY
+#define RCED_TC_BOUNDARY 1
+#endif
+struct NextIn {       // what the staging of the next batch needs (prefetched by warp 4)
+    const float* ib;  // its kFB + 7 input rows
+    const int* tm8;   // per frame: mask of the time taps inside its utterance
+    const float* fsc; // per frame: power-of-two scale
+    int nf;           // frames of the next batch (0: there is none)
+};
 template <int ARCH>
-__device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const uint32_t par) {
+__device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const uint32_t par, const NextIn& nx, uint32_t& amax2) {
     constexpr int s = num_layers(ARCH) - 1;
-    mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 300);
+#if RCED_TC_BOUNDARY
+    if (nx.nf > 0)
+        mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t)),
+                   bar_addr(c, kBarAccFull + (t > 0 ? t - 1 : t)), par, c.err, 300);
+    else
+#endif
+        mbar_wait(bar_addr(c, kBarAccFull + t), par, c.err, 300);
     fence_after();
     stamp(c.trace, c.tracing && c.quad == 0 && c.lane == 0, s, t, 2);
     const int r0 = t * 128 + c.quad * 32;
@@ -672,6 +693,25 @@ __device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const 
         if (vb && (fb & 1) == odd) c.outp[kRows + rb] = tot - own;
     }
     if (c.tracing && c.quad == 0 && c.lane == 0) stamp(c.trace, true, s, t, 3);
+#if RCED_TC_BOUNDARY
+    if (nx.nf > 0) {
+        // first-layer input of the next batch, this thread's row: "channel" = time tap, rows g-3 .. g+4 of the utterance
+        const int r = t * 128 + c.quad * 32 + c.lane;
+        const int fi = r / kFS, b = r - fi * kFS;
+        float v[8];
+        if (fi < nx.nf && b < kBins) {
+            const int m = nx.tm8[fi];
+            const float sfi = nx.fsc[fi];   // into the frame's scaled domain (a power of two: exact)
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) v[tt] = (m >> tt) & 1 ? nx.ib[(fi + tt) * kInStride + b] * sfi : 0.f;
+        } else {
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) v[tt] = 0.f;
+        }
+        store_split8(c.act, 0, kLead + r, v, true, amax2);
+        fence_async_smem();   // plane writes visible to the tensor core (async proxy)
+    }
+#endif
     fence_before();
     __syncwarp();
     if (c.lane == 0) mbar_arrive(bar_addr(c, kBarActReady + t));
@@ -900,9 +940,10 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         bool bad_input = false;
         for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++itn) {
             if (itn >= 2) {
-                // buffer itn & 1 was read by the staging of batch itn - 2: wait until the scout has
-                // seen that batch's input barrier (its counter has then passed the batch's first tile)
-                const uint32_t need = (itn - 2) * NS * kTiles + 1;
+                // buffer itn & 1 was read by the staging of batch itn - 2: wait until the scout has cleared every row
+                // tile of that batch's first layer (the staging of its last tile has then been released; round-1 form:
+                // its counter has passed the input barrier, i.e. the batch's first tile)
+                const uint32_t need = (itn - 2) * NS * kTiles + (RCED_TC_BOUNDARY ? kTiles : 1);
                 for (int spin = 0; ld_acquire(flag) < need; ++spin) {
                     __nanosleep(200);
                     if ((spin & 255) == 255 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
@@ -977,7 +1018,9 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
 #pragma unroll 1
                     for (int t = 0; t < kTiles; ++t) {
                         if (t == 0) {
-                            if (s == 0) mbar_wait(bars + 8 * kBarInReady, it & 1, err, 1);
+                            // first layer: its input is staged (the first batch: by all epilogue warps up front; later
+                            // batches with RCED_TC_BOUNDARY: by the output layer's epilogues, covered by act_ready below)
+                            if (s == 0 && (!RCED_TC_BOUNDARY || it == 0)) mbar_wait(bars + 8 * kBarInReady, it & 1, err, 1);
                             mbar_wait(bars + 8 * (kBarWFull + wb), (k >> 1) & 1, err, 2);
                             if (k > 0) mbar_wait(bars + 8 * (kBarActReady + 0), (k - 1) & 1, err, 3);
                         }
@@ -1066,12 +1109,27 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             {
                 const uint32_t par = (k0 + NL - 1) & 1;
                 static_assert(kTiles == 2 * kGroups, "two row tiles per epilogue group");
-                epi_final_tile<ARCH>(c, c.grp, par);
+                NextIn nx{nullptr, nullptr, nullptr, 0};
+#if RCED_TC_BOUNDARY
+                if (batch + gridDim.x < NB) {
+                    const uint32_t sit = it + 1;
+                    const long long left_n = p.total_rows - (batch + gridDim.x) * kFB;
+                    for (int spin = 0; ld_acquire(bars + 8 * kNextInSlot) <= sit; ++spin)   // the prefetch warp has the batch
+                        if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
+                    nx.ib = reinterpret_cast<const float*>(smem + smem_in_off(ARCH)) + (sit & 1) * kInRows * kInStride;
+                    nx.tm8 = reinterpret_cast<const int*>(bnd) + (sit & 1) * 8;
+                    nx.fsc = s_scale + (sit & (kScaleRing - 1)) * 8;
+                    nx.nf = left_n < kFB ? (int)left_n : kFB;
+                }
+                epi_final_tile<ARCH>(c, c.grp, par, nx, amax2);
+#else
+                epi_final_tile<ARCH>(c, c.grp, par, nx, amax2);
                 if (batch + gridDim.x < NB) {
                     mbar_wait(bars + 8 * kBarFinalDone, it & 1, err, 6);
                     stage_input(batch + gridDim.x, it + 1);
                 }
-                epi_final_tile<ARCH>(c, c.grp + kGroups, par);
+#endif
+                epi_final_tile<ARCH>(c, c.grp + kGroups, par, nx, amax2);
             }
             epi_bar();   // both partial sums of every output row are stored
             for (int i = c.et; i < c.nf * kBins; i += 32 * kEpiWarps) {

@@ -2,11 +2,12 @@
 
 The kernel (csrc/rced_net_tc.cu) updates its activation planes in place while MMAs of neighbouring row
 tiles, of the next layer and of the next batch are in flight; what keeps that safe is a handful of waits
-(the three commits an epilogue awaits, the scout's cumulative act_ready waits, final_done before the next
-batch is staged, in_ready before its first layer, w_free / w_full of the weight double buffer).  This test
-rebuilds those waits as a graph over the events of two consecutive batches -- M(b,s,t): the MMAs of (step,
-row tile); E(b,s,t): its epilogue; S(b,g): epilogue group g staging batch b's input; W(b,s): the producer's
-copy of step s's weights -- takes the rows and planes every event reads and writes from the library's own
+(the three commits an epilogue awaits -- the output layer's epilogue too, because it stages the next batch's
+input for its row tile in place --, the scout's cumulative act_ready waits, in_ready before the first layer of
+a CTA's first batch, w_free / w_full of the weight double buffer).  This test rebuilds those waits as a graph
+over the events of two consecutive batches -- M(b,s,t): the MMAs of (step, row tile); E(b,s,t): its epilogue
+(for the output layer of batch 0: including the staging of batch 1's rows of tile t); S(0,g): epilogue group g
+staging the first batch's input; W(b,s): the producer's copy of step s's weights -- takes the rows and planes every event reads and writes from the library's own
 layout tables (rced_tc_layout), and asserts that every pair of conflicting accesses (plane write vs plane
 read or write on overlapping rows; accumulator write vs read; weight buffer write vs read) is ordered by
 the transitive closure.  It would have caught the race of the two-commit wait with three issuing threads
@@ -54,7 +55,7 @@ def _accesses(name):
     return steps
 
 
-def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_waits_final_done=True,
+def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, final_waits_neighbours=True,
            producer_waits_w_free=True):
     ns = len(steps)
     nodes, edges = [], {}
@@ -69,8 +70,9 @@ def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_wa
         edges[node(*u)].add(node(*v))
 
     for b in range(2):
-        for g in range(GROUPS):
-            node("S", b, g)
+        if b == 0:
+            for g in range(GROUPS):
+                node("S", b, g)
         for s in range(ns):
             for t in range(TILES):
                 node("M", b, s, t)
@@ -79,7 +81,10 @@ def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_wa
         for s in range(ns):
             for t in range(TILES):
                 # epilogue waits (mbar_wait3 / the output layer's single wait)
-                need = [t] if steps[s]["final"] else [t, t + 1] + ([t - 1] if wait_prev_tile else [])
+                if steps[s]["final"]:      # stages the next batch's rows of tile t if there is a next batch (b == 0)
+                    need = [t] + ([t + 1, t - 1] if b == 0 and final_waits_neighbours else [])
+                else:
+                    need = [t, t + 1] + ([t - 1] if wait_prev_tile else [])
                 for tt in need:
                     if 0 <= tt < TILES:
                         before(("M", b, s, tt), ("E", b, s, t))
@@ -88,17 +93,14 @@ def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_wa
                 if prev is not None:
                     for tt in range(0, min(t + 1, TILES - 1) + 1):
                         before(("E", prev[0], prev[1], tt), ("M", b, s, t))
-                if s == 0:                                    # in_ready: every group has staged
+                if s == 0 and b == 0:                         # in_ready (first batch only): every group has staged
                     for g in range(GROUPS):
                         before(("S", b, g), ("M", b, 0, t))
-        # program order of an epilogue group: tiles g, g + 4 of every step; staging between the two
-        # output-layer tiles
+        # program order of an epilogue group: tiles g, g + 4 of every step
         for g in range(GROUPS):
             seq = [("S", 0, g)] if b == 0 else []
             for s in range(ns):
                 seq.append(("E", b, s, g))
-                if s == ns - 1 and b == 0:
-                    seq.append(("S", 1, g))
                 seq.append(("E", b, s, g + GROUPS))
             if b == 1:
                 seq = [("E", 0, ns - 1, g + GROUPS)] + seq
@@ -120,10 +122,6 @@ def _build(steps, wait_prev_tile=True, scout_waits_final_epilogue=True, stage_wa
                 before(("W", pb, ps), ("W", b, s))
             for t in range(TILES):
                 before(("W", b, s), ("M", b, s, t))
-    if stage_waits_final_done:                                # final_done: every MMA of the output layer
-        for g in range(GROUPS):
-            for t in range(TILES):
-                before(("M", 0, ns - 1, t), ("S", 1, g))
     return nodes, edges
 
 
@@ -169,7 +167,10 @@ def _races(steps, **variant):
             return {(0, r) for r in range(128 * TILES)}       # plane 0, every row (each group: interleaved rows)
         if n[0] == "E":
             _, b, s, t = n
-            return {(p, r) for p in steps[s]["writes"] for r in range(128 * t, 128 * t + 128)}
+            planes = steps[s]["writes"]
+            if steps[s]["final"] and b == 0:                  # the next batch's first-layer input, rows of this tile
+                planes = {0}
+            return {(p, r) for p in planes for r in range(128 * t, 128 * t + 128)}
         return set()
 
     acc_w = {n: n[3] for n in nodes if n[0] == "M"}
@@ -204,5 +205,5 @@ def test_model_detects_the_known_protocol_bugs():
     r = _races(steps, wait_prev_tile=False)                   # the two-commit wait (tile t-1's MMAs read tile t's halo)
     assert any(u[0] != v[0] and {u[0], v[0]} == {"M", "E"} for u, v in r)
     assert _races(steps, scout_waits_final_epilogue=False)    # next batch's first layer overwrites unread accumulators
-    assert _races(steps, stage_waits_final_done=False)        # staging plane 0 under the output layer's MMAs
+    assert _races(steps, final_waits_neighbours=False)        # staging tile t's rows under the output layer's MMAs of tiles t-1, t+1
     assert _races(steps, producer_waits_w_free=False)         # weights of step s+2 land under the MMAs of step s

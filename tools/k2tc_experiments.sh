@@ -14,6 +14,7 @@ VARIANTS=(
   "l2hint:-DRCED_TC_SKIPHINT=1"
   "l1bypass:-DRCED_TC_SKIPHINT=3"
   "validrows:-DRCED_TC_DIAG_VALIDROWS"
+  "boundary0:-DRCED_TC_BOUNDARY=0"
   "skipbulk:-DRCED_TC_SKIP_BULK=1"
   "skipdeferred:-DRCED_TC_SAVE_DEFERRED"
   "noskip_DIAG:-DRCED_TC_DIAG_NOSKIP"
