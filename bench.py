@@ -356,6 +356,9 @@ def main():
                     help="one job of this many 4 s utterances partitioned over the ranks (BASELINE.json configs[4]), device-"
                          "resident, reported under 'sweep' (0: skip)")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--relay", default="auto", choices=["auto", "off"],
+                    help="multi-GPU: measure every GPU's host link with all ranks copying at once and let ranks on a slow / shared "
+                         "link move their waveforms through a fast peer GPU (rced_host_set_relay); off: every rank copies directly")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -473,9 +476,59 @@ def main():
             step_device(evs[i])
         b.record()
         barrier()
-        ms = max_over_ranks(a.elapsed_time(b))
+        mine = a.elapsed_time(b)
+        ms = max_over_ranks(mine)
         per = [float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])) for j in range(3)]
+        per.append(per_rank(mine / n_steps))
         return ms, per
+
+    # ---------------- host links (multi-GPU): who copies through whom ---------------------------
+    from fullycnnspeechenhancement_b200.engine import plan_relays, relay_candidates
+    link, link_fast_only, relay_of = None, None, None
+    if world > 1:
+        # Every rank copies its own page-locked buffers both ways at the same time (the buffers exist already: the timed
+        # copies start right behind the barrier on all ranks and run for ~100 ms).  If that shows ranks whose link is too slow
+        # for their stream, a second pass with only the other ranks copying shows what THEIR links give once the slow ranks'
+        # traffic is gone -- i.e. whether they can carry a second stream as relays.
+        t_in, t_out = torch.from_numpy(h_wav[0]), torch.from_numpy(h_out[0])
+        assert t_in.is_pinned() and t_out.is_pinned()
+        sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        reps = 6
+
+        def copy_pass(active):
+            got = (0.0, 0.0)
+            for timed in (False, True):
+                barrier()
+                if active:
+                    with torch.cuda.stream(sa):
+                        ev[0].record()
+                        for _ in range(reps):
+                            d_wav.copy_(t_in, non_blocking=True)
+                        ev[1].record()
+                    with torch.cuda.stream(sb):
+                        ev[2].record()
+                        for _ in range(reps):
+                            t_out.copy_(d_out, non_blocking=True)
+                        ev[3].record()
+                    torch.cuda.synchronize()
+                    got = (reps * total * 4 / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9, reps * total * 4 / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
+            barrier()
+            return [list(x) for x in zip(per_rank(got[0]), per_rank(got[1]))]
+
+        link = copy_pass(True)
+        needed = total * 4 / 14.0e-3 / 1e9              # one direction's bytes per ~14 ms step
+        worst = [min(a, b) for a, b in link]
+        slow, fast = relay_candidates(worst, needed)
+        relay_of = [-1] * world
+        if args.relay == "auto" and slow:
+            link_fast_only = copy_pass(rank in fast)
+            relay_of = plan_relays(worst, needed, relay_gbs=[min(a, b) for a, b in link_fast_only])
+        if os.environ.get("RCED_BENCH_FORCE_RELAY"):      # experiment: "4,5,6,7,-1,-1,-1,-1"
+            relay_of = [int(x) for x in os.environ["RCED_BENCH_FORCE_RELAY"].split(",")]
+        if relay_of[rank] >= 0:
+            eng.host_set_relay(relay_of[rank])           # ranks are local GPU indices on one node
+        barrier()
 
     # measured FP32 FFMA peak of this GPU (the roofline denominator; MEASURED_PEAKS.json has none)
     tf = ctypes.c_double()
@@ -491,7 +544,7 @@ def main():
         sampler.start()
         time.sleep(0.25)
     launches0 = lib.rced_launch_count()
-    ms_total, (k1_ms, k2_ms, k3_ms) = timed_device_steps(args.steps, 0)
+    ms_total, (k1_ms, k2_ms, k3_ms, dev_rank_ms) = timed_device_steps(args.steps, 0)
     launches = lib.rced_launch_count() - launches0
     audio_s_per_step = N_UTT * UTT_SAMPLES / SAMPLE_RATE
     value = world * audio_s_per_step * args.steps / (ms_total * 1e-3)
@@ -528,7 +581,7 @@ def main():
     # ---------------- the other network kernel, a few steps ------------------------------------
     eng.set_variant(other)
     o_steps = max(3, min(args.steps, 5))
-    o_ms_total, (_, o_k2_ms, _) = timed_device_steps(o_steps, 2)
+    o_ms_total, (_, o_k2_ms, _, _) = timed_device_steps(o_steps, 2)
     o_value = world * audio_s_per_step * o_steps / (o_ms_total * 1e-3)
     eng.set_variant(args.variant)
 
@@ -574,7 +627,8 @@ def main():
         ffma_roof, ffma_value, ffma_steps = main_roof, value, args.steps
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "ms_per_step_by_rank": dev_rank_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16x3 (FP16 hi/lo split, 3 products per multiply, FP32 accumulate; scale-invariant, 1e-6 of float64)"
                  if args.variant == "tc" else "f32",
         "data": "synthetic (64 seeded tone/chirp + white/babble-noise utterances tiled to 1024 per GPU)",
@@ -592,6 +646,10 @@ def main():
                 "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": total * 4,
                 "ms_per_step_by_rank": e2e_rank_ms, "gpu_numa_node_by_rank": [int(x) for x in numa_nodes],
                 "host_cores": host_cores(),
+                "host_link_gbs_by_rank": link, "host_link_gbs_fast_ranks_only": link_fast_only, "relay_gpu_by_rank": relay_of,
+                "relay_note": None if not relay_of or max(relay_of) < 0 else
+                              "ranks with a relay move their waveforms host -> relay GPU -> NVLink -> own GPU and back "
+                              "(rced_host_set_relay): their own path to host memory is shared and too slow for the stream",
                 "api": "rced_enhance_host_async (Enhancer.enhance_host): page-locked host waveforms -> H2D -> K1, K2, K3 -> D2H -> "
                        "page-locked host output, chunks of ~131072 spectrogram rows through the library's copy-in / compute / "
                        "copy-out streams; the steps alternate between two host buffer sets and are queued behind each other, "

@@ -49,6 +49,9 @@ SIGNATURES = {
     "rced_enhance_host_async": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_int, c_p, c_p, c_p]),
     "rced_host_sync": (ctypes.c_int, [c_p]),
     "rced_host_config": (ctypes.c_int, [c_p, c_i64, c_i64]),
+    "rced_host_set_relay": (ctypes.c_int, [c_p, ctypes.c_int]),
+    "rced_host_link_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_double)]),
     "rced_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(c_p)]),
     "rced_host_free": (ctypes.c_int, [c_p]),
     "rced_mag_phase": (ctypes.c_int, [ctypes.c_int, c_p, c_i64, c_p, c_p, c_p]),

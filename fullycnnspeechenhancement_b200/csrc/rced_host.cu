@@ -18,6 +18,13 @@
 // Caller's buffers: any host memory works (cudaMemcpyAsync); page-locked memory (cudaHostAlloc /
 // cudaHostRegister / torch pin_memory) is what makes the copies asynchronous and the chunks overlap.
 //
+// Relay (rced_host_set_relay): on multi-GPU boxes some GPUs reach host memory through a shared, slower link than
+// others (measured on the 8 x B200 box of this project: 7.8 GB/s per direction for four of the GPUs against > 20 GB/s
+// for the other four).  A handle on such a GPU can move its waveforms through a PEER GPU of the
+// same process instead: H2D into a staging buffer on the relay device, then cudaMemcpyPeerAsync over NVLink into the
+// handle's own buffer (and the same way back).  The relay's copy engines do the work; the handle's kernels and the
+// relay device's own users are not involved.
+//
 // Range guard of the tensor-core network kernel: the device-pointer ABI queues the FP32 kernel behind every
 // tensor-core launch (it returns at once unless the guard tripped).  The host pipeline copies each launch's guard
 // words to page-locked memory instead and looks at them when it synchronises: a chunk whose guard tripped
@@ -51,6 +58,10 @@ struct BufferSet {
     cudaEvent_t uploaded = nullptr;    // copy-in:  the set's waveforms and tables are on the device (h_meta may be refilled)
     cudaEvent_t computed = nullptr;    // compute:  K1-K3 done (d_wav / d_meta may be overwritten, d_out may be downloaded)
     cudaEvent_t downloaded = nullptr;  // copy-out: d_out has left (the next K3 of this set may write it)
+    // relay mode: staging on the relay device and the events of its two streams
+    float *r_in = nullptr, *r_out = nullptr;
+    size_t cap_r_in = 0, cap_r_out = 0;
+    cudaEvent_t r_uploaded = nullptr, r_downloaded = nullptr;
 };
 
 struct PendingChunk {   // what is needed to recompute a chunk whose range guard tripped
@@ -74,6 +85,9 @@ struct HostPipe {
     unsigned int* h_flags = nullptr;   // page-locked [kPendingMax][2]: guard words of the pending tensor-core launches
     std::vector<PendingChunk> pending;
     bool recomputing = false;
+    int relay = -1;                    // device whose copy engines carry the waveforms (-1: the handle's own)
+    int relay_made_on = -1;            // device the relay streams / events / staging were created on
+    cudaStream_t r_in = nullptr, r_out = nullptr;   // streams on the relay device
 };
 
 static size_t grow(size_t need) { return need + need / 4 + 256; }
@@ -90,9 +104,16 @@ void host_pipe_destroy(HostPipe* p) {
         cudaFree(b.ws_pred);
         cudaFree(b.d_meta);
         if (b.h_meta) cudaFreeHost(b.h_meta);
-        for (cudaEvent_t e : {b.uploaded, b.computed, b.downloaded})
+        for (cudaEvent_t e : {b.uploaded, b.computed, b.downloaded, b.r_uploaded, b.r_downloaded})
             if (e) cudaEventDestroy(e);
+        cudaFree(b.r_in);    // (cudaFree finds the owning device by itself)
+        cudaFree(b.r_out);
     }
+    for (cudaStream_t s : {p->r_in, p->r_out})
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
     for (cudaStream_t s : {p->s_in, p->s_compute, p->s_out})
         if (s) cudaStreamDestroy(s);
     if (p->h_flags) cudaFreeHost(p->h_flags);
@@ -213,9 +234,35 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
     // ---- copy-in: behind the kernels that read this set's previous waveforms and tables
     // development aid (tools/e2e_sweep.py): RCED_HOST_NOCOPY=1 leaves the waveform copies out to see what they cost
     static const bool no_copy = getenv("RCED_HOST_NOCOPY") != nullptr;
+    const bool relay = pipe->relay >= 0 && !pipe->recomputing;
+    const size_t in_bytes = (size_t)(in_hi - in_lo) * sizeof(float), out_bytes = (size_t)(o_hi - o_lo) * sizeof(float);
     cudaStreamWaitEvent(pipe->s_in, b.computed, 0);
-    if (!no_copy &&
-        (e = cudaMemcpyAsync(b.d_wav, wav + in_lo, (size_t)(in_hi - in_lo) * sizeof(float), cudaMemcpyHostToDevice, pipe->s_in)) != cudaSuccess)
+    if (relay && !no_copy) {
+        // host -> relay device (its link to the host) -> this device (NVLink), on the relay's copy-in stream
+        cudaSetDevice(pipe->relay);
+        e = cudaSuccess;
+        if (in_bytes > b.cap_r_in) {
+            cudaFree(b.r_in);
+            b.r_in = nullptr;
+            b.cap_r_in = 0;
+            if ((e = cudaMalloc(&b.r_in, grow(in_bytes))) == cudaSuccess) b.cap_r_in = grow(in_bytes);
+        }
+        if (e == cudaSuccess && out_bytes > b.cap_r_out) {
+            cudaFree(b.r_out);
+            b.r_out = nullptr;
+            b.cap_r_out = 0;
+            if ((e = cudaMalloc(&b.r_out, grow(out_bytes))) == cudaSuccess) b.cap_r_out = grow(out_bytes);
+        }
+        if (e == cudaSuccess) {
+            cudaStreamWaitEvent(pipe->r_in, b.computed, 0);   // the kernels that read d_wav before have finished
+            e = cudaMemcpyAsync(b.r_in, wav + in_lo, in_bytes, cudaMemcpyHostToDevice, pipe->r_in);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(b.d_wav, h->device, b.r_in, pipe->relay, in_bytes, pipe->r_in);
+        if (e == cudaSuccess) e = cudaEventRecord(b.r_uploaded, pipe->r_in);
+        cudaSetDevice(h->device);
+        if (e != cudaSuccess) return cuda_fail(e, "host pipeline: H2D waveforms through the relay device");
+    } else if (!no_copy &&
+        (e = cudaMemcpyAsync(b.d_wav, wav + in_lo, in_bytes, cudaMemcpyHostToDevice, pipe->s_in)) != cudaSuccess)
         return cuda_fail(e, "host pipeline: H2D waveforms");
     if ((e = cudaMemcpyAsync(dm, hm, meta_bytes, cudaMemcpyHostToDevice, pipe->s_in)) != cudaSuccess) return cuda_fail(e, "host pipeline: H2D tables");
     cudaEventRecord(b.uploaded, pipe->s_in);
@@ -228,6 +275,10 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
     const int32_t* d_out_len = reinterpret_cast<const int32_t*>(dm + o_out_len);
     cudaStreamWaitEvent(pipe->s_compute, b.uploaded, 0);
     cudaStreamWaitEvent(pipe->s_compute, b.downloaded, 0);
+    if (pipe->relay >= 0) {   // (events that were never recorded are complete)
+        cudaStreamWaitEvent(pipe->s_compute, b.r_uploaded, 0);
+        cudaStreamWaitEvent(pipe->s_compute, b.r_downloaded, 0);
+    }
     int rc = rced_stft(h, b.d_wav, d_wav_off, d_wav_len, d_row_off, n, rows, b.ws_mag, b.ws_phase, pipe->s_compute);
     if (rc != RCED_OK) return rc;
     unsigned int* d_flags = nullptr;
@@ -246,8 +297,16 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
     }
     e = cudaSuccess;
     if (no_copy) {
+    } else if (out_contiguous && relay) {
+        // this device -> relay device (NVLink) -> host, on the relay's copy-out stream
+        cudaSetDevice(pipe->relay);
+        cudaStreamWaitEvent(pipe->r_out, b.computed, 0);
+        e = cudaMemcpyPeerAsync(b.r_out, pipe->relay, b.d_out, h->device, out_bytes, pipe->r_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + o_lo, b.r_out, out_bytes, cudaMemcpyDeviceToHost, pipe->r_out);
+        if (e == cudaSuccess) e = cudaEventRecord(b.r_downloaded, pipe->r_out);
+        cudaSetDevice(h->device);
     } else if (out_contiguous) {
-        e = cudaMemcpyAsync(out + o_lo, b.d_out, (size_t)(o_hi - o_lo) * sizeof(float), cudaMemcpyDeviceToHost, pipe->s_out);
+        e = cudaMemcpyAsync(out + o_lo, b.d_out, out_bytes, cudaMemcpyDeviceToHost, pipe->s_out);
     } else {   // gaps between the outputs belong to the caller: copy utterance by utterance
         for (int u = c0; u < c1 && e == cudaSuccess; ++u)
             e = cudaMemcpyAsync(out + out_off[u], b.d_out + (out_off[u] - o_lo), (size_t)out_len[u] * sizeof(float), cudaMemcpyDeviceToHost, pipe->s_out);
@@ -259,7 +318,8 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
 static int host_sync_impl(rced_handle* h) {
     HostPipe* p = h->pipe;
     if (!p) return RCED_OK;
-    for (cudaStream_t s : {p->s_in, p->s_compute, p->s_out}) {
+    for (cudaStream_t s : {p->s_in, p->s_compute, p->s_out, p->r_in, p->r_out}) {
+        if (!s) continue;
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return cuda_fail(e, "rced_host_sync");
     }
@@ -349,6 +409,108 @@ int rced_host_config(rced_handle* h, int64_t chunk_rows, int64_t chunk_rows_asyn
     p->chunk_rows = chunk_rows;
     p->chunk_rows_async = chunk_rows_async;
     return RCED_OK;
+}
+
+int rced_host_set_relay(rced_handle* h, int relay_device) {
+    if (!h) return fail(RCED_ERR_ARG, "null handle");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) return fail(RCED_ERR_CUDA, "no CUDA device");
+    if (relay_device >= ndev || relay_device == h->device) return fail(RCED_ERR_ARG, "relay must be another visible device (or -1)");
+    DeviceGuard guard(h->device);
+    HostPipe* p = nullptr;
+    int rc = pipe_get(h, &p);
+    if (rc != RCED_OK) return rc;
+    rc = host_sync_impl(h);   // nothing in flight while the route changes
+    if (rc != RCED_OK) return rc;
+    if (relay_device < 0) {
+        p->relay = -1;
+        return RCED_OK;
+    }
+    if (p->r_in && p->relay_made_on != relay_device) {   // a different relay than before: its streams, events and staging go
+        for (BufferSet& b : p->set) {
+            cudaFree(b.r_in);
+            cudaFree(b.r_out);
+            b.r_in = b.r_out = nullptr;
+            b.cap_r_in = b.cap_r_out = 0;
+            for (cudaEvent_t* ev : {&b.r_uploaded, &b.r_downloaded})
+                if (*ev) {
+                    cudaEventDestroy(*ev);
+                    *ev = nullptr;
+                }
+        }
+        cudaStreamDestroy(p->r_in);
+        cudaStreamDestroy(p->r_out);
+        p->r_in = p->r_out = nullptr;
+    }
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, h->device, relay_device);
+    if (!can) return fail(RCED_ERR_STATE, "the relay device is not a peer of the handle's device");
+    cudaError_t e = cudaDeviceEnablePeerAccess(relay_device, 0);   // own device -> relay
+    if (e == cudaErrorPeerAccessAlreadyEnabled) e = cudaGetLastError(), e = cudaSuccess;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    cudaSetDevice(relay_device);
+    e = cudaDeviceEnablePeerAccess(h->device, 0);                  // relay -> own device
+    if (e == cudaErrorPeerAccessAlreadyEnabled) e = cudaGetLastError(), e = cudaSuccess;
+    if (e == cudaSuccess && !p->r_in) e = cudaStreamCreateWithFlags(&p->r_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess && !p->r_out) e = cudaStreamCreateWithFlags(&p->r_out, cudaStreamNonBlocking);
+    for (BufferSet& b : p->set)
+        for (cudaEvent_t* ev : {&b.r_uploaded, &b.r_downloaded})
+            if (e == cudaSuccess && !*ev) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(e, "relay set-up");
+    p->relay = relay_device;
+    p->relay_made_on = relay_device;
+    return RCED_OK;
+}
+
+int rced_host_link_probe(int device, size_t bytes, int iters, double* h2d_gbs, double* d2h_gbs) {
+    if (!h2d_gbs || !d2h_gbs || bytes == 0 || iters < 1) return fail(RCED_ERR_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(RCED_ERR_CUDA, "no such CUDA device");
+    DeviceGuard guard(device);
+    void *h_a = nullptr, *h_b = nullptr, *d_a = nullptr, *d_b = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, f0 = nullptr, f1 = nullptr;
+    cudaError_t e = cudaHostAlloc(&h_a, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h_b, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&d_a, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_b, bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+    for (cudaEvent_t* ev : {&e0, &e1, &f0, &f1})
+        if (e == cudaSuccess) e = cudaEventCreate(ev);
+    if (e == cudaSuccess) {
+        memset(h_a, 0, bytes);
+        // both directions at once, like the pipeline in steady state; one warm-up pass
+        for (int pass = 0; pass < 2 && e == cudaSuccess; ++pass) {
+            cudaEventRecord(e0, s0);
+            cudaEventRecord(f0, s1);
+            for (int i = 0; i < iters; ++i) {
+                cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s0);
+                cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s1);
+            }
+            cudaEventRecord(e1, s0);
+            cudaEventRecord(f1, s1);
+            e = cudaStreamSynchronize(s0);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s1);
+        }
+        if (e == cudaSuccess) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, e0, e1);
+            cudaEventElapsedTime(&b, f0, f1);
+            *h2d_gbs = (double)bytes * iters / (a * 1e-3) / 1e9;
+            *d2h_gbs = (double)bytes * iters / (b * 1e-3) / 1e9;
+        }
+    }
+    for (cudaEvent_t ev : {e0, e1, f0, f1})
+        if (ev) cudaEventDestroy(ev);
+    if (s0) cudaStreamDestroy(s0);
+    if (s1) cudaStreamDestroy(s1);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    if (h_a) cudaFreeHost(h_a);
+    if (h_b) cudaFreeHost(h_b);
+    return e == cudaSuccess ? RCED_OK : cuda_fail(e, "rced_host_link_probe");
 }
 
 int rced_host_alloc(size_t bytes, int write_combined, void** out) {

@@ -97,6 +97,41 @@ class PinnedArray(object):
             pass
 
 
+def host_link_probe(device, n_bytes=64 << 20, iters=4):
+    """(H2D GB/s, D2H GB/s) of `device`'s link to page-locked host memory, both directions busy (rced_host_link_probe)."""
+    a, b = ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.lib().rced_host_link_probe(int(device), int(n_bytes), int(iters), ctypes.byref(a), ctypes.byref(b)))
+    return float(a.value), float(b.value)
+
+
+def relay_candidates(link_gbs, needed_gbs, slow_factor=0.8):
+    """(slow, fast): ranks whose host link -- measured with ALL ranks copying at once -- is too slow for their own stream
+    (< needed_gbs per direction) and clearly slower than the best one (< slow_factor x best), slowest first; and the other
+    ranks, fastest first.  Every rank computes the same lists."""
+    n = len(link_gbs)
+    best = max(link_gbs)
+    slow = sorted((r for r in range(n) if link_gbs[r] < needed_gbs and link_gbs[r] < slow_factor * best), key=lambda r: link_gbs[r])
+    fast = sorted((r for r in range(n) if r not in slow), key=lambda r: -link_gbs[r])
+    return slow, fast
+
+
+def plan_relays(link_gbs, needed_gbs, relay_gbs=None, slow_factor=0.8, headroom=2.0):
+    """Which ranks should move their waveforms through which peer GPU (rced_host_set_relay).  ``link_gbs[r]``: the slower
+    direction of rank r's host link with all ranks copying at once; ``needed_gbs``: what one rank's stream needs per
+    direction to stay hidden behind its kernels; ``relay_gbs[r]``: the same measurement with ONLY the fast ranks copying
+    (what their links give once the slow ranks' traffic no longer crosses the shared path), None: use ``link_gbs``.  A slow
+    rank (``relay_candidates``) is paired with a fast rank whose link carries ``headroom x needed_gbs`` -- its own stream plus
+    the guest's.  Returns relay[r] = rank whose GPU carries r's copies, or -1; every rank computes the same answer."""
+    n = len(link_gbs)
+    slow, fast = relay_candidates(link_gbs, needed_gbs, slow_factor)
+    cap = link_gbs if relay_gbs is None else relay_gbs
+    fast = [r for r in fast if cap[r] >= headroom * needed_gbs]
+    relay = [-1] * n
+    for s, f in zip(slow, fast):
+        relay[s] = f
+    return relay
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -310,6 +345,10 @@ class Enhancer(object):
     def host_config(self, chunk_rows=32768, chunk_rows_async=None):
         """Target spectrogram rows per chunk of the host pipeline, for synchronous and for asynchronous calls."""
         _lib.check(self.lib.rced_host_config(self._h, int(chunk_rows), int(chunk_rows_async or chunk_rows)))
+
+    def host_set_relay(self, relay_device):
+        """Route the host-buffer calls' waveform copies through a peer GPU (-1: direct).  See rced_host_set_relay."""
+        _lib.check(self.lib.rced_host_set_relay(self._h, int(relay_device)))
 
     def _stage(self, total):
         """Persistent page-locked staging (input, output), grown geometrically: enhance() never pins per call."""

@@ -215,6 +215,16 @@ int rced_enhance_host_async(rced_handle* h, const float* wav, const int64_t* wav
 int rced_host_sync(rced_handle* h);
 int rced_host_config(rced_handle* h, int64_t chunk_rows, int64_t chunk_rows_async);
 
+/* Route the waveform copies of the host-buffer calls through a PEER GPU of this process: host -> relay device (its own
+ * link to the host) -> NVLink -> the handle's device, and back the same way.  For boxes on which some GPUs reach host
+ * memory through a slower or shared link than others (measure first: bench.py does).  relay_device = -1 restores the
+ * direct route.  Synchronises the handle's host pipeline.  RCED_ERR_STATE if the two devices are not peers. */
+int rced_host_set_relay(rced_handle* h, int relay_device);
+
+/* Bandwidth of `device`'s link to page-locked host memory with both directions busy (GB/s each), `iters` copies of `bytes`
+ * per direction.  Run on all GPUs of a box at the same time it shows which of them share a slower link. */
+int rced_host_link_probe(int device, size_t bytes, int iters, double* h2d_gbs, double* d2h_gbs);
+
 /* Page-locked host memory for the buffers above (cudaHostAlloc), for callers that have no other way to pin memory.
  * write_combined != 0: write-combined memory -- faster for the device to read, very slow for the CPU to read: for
  * INPUT buffers the host only writes. */

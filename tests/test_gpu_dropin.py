@@ -267,3 +267,30 @@ def test_host_entry_point_recomputes_a_tripped_chunk_with_the_fp32_kernel():
         assert np.array_equal(x, y)
     tc.close()
     fp32.close()
+
+
+def test_host_entry_point_through_a_relay_device():
+    """rced_host_set_relay: the waveforms travel host -> peer GPU -> NVLink -> the handle's GPU and back; results are
+    bit-identical to the direct route.  Needs two GPUs that are peers."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from fullycnnspeechenhancement_b200 import _lib
+    from fullycnnspeechenhancement_b200.synth import noisy_utterance
+    eng, _ = _host_eng(seed=78)
+    waves = [noisy_utterance(700 + i, 2000 + 811 * i) for i in range(9)]
+    eng.host_config(chunk_rows=100)
+    direct = eng.enhance(waves)
+    try:
+        eng.host_set_relay(1)
+    except _lib.RcedError as exc:
+        if exc.code == _lib.ERR_STATE:
+            pytest.skip("GPUs 0 and 1 are not peers")
+        raise
+    via = eng.enhance(waves)
+    again = eng.enhance(waves)
+    eng.host_set_relay(-1)
+    back = eng.enhance(waves)
+    for a, b, c, d in zip(direct, via, again, back):
+        assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
+    eng.close()

@@ -411,3 +411,21 @@ def test_host_tables_follow_the_reference_truncation():
         host_tables(np.array([10, 0]))
     with pytest.raises(ValueError):
         host_tables(np.array([10, 20]), out_lens=[5])
+
+
+def test_relay_plan():
+    """Which ranks copy through which peer GPU.  The box of this project: with all eight ranks copying, GPUs 0-3 get
+    8 GB/s per direction (their path to host memory is shared), GPUs 4-7 get 11 GB/s; with only GPUs 4-7 copying those reach
+    > 20 GB/s: slow_i -> fast_i.  Uniform boxes, and boxes whose fast links cannot carry two streams, get no relay."""
+    from fullycnnspeechenhancement_b200.engine import plan_relays, relay_candidates
+    need = 9.4
+    all_busy = [8.0, 8.1, 7.9, 8.0, 11.2, 11.1, 11.3, 11.2]
+    slow, fast = relay_candidates(all_busy, need)
+    assert slow == [2, 0, 3, 1] and fast == [6, 4, 7, 5]
+    assert plan_relays(all_busy, need) == [-1] * 8                          # judged by the saturated figures alone: no
+    got = plan_relays(all_busy, need, relay_gbs=[0, 0, 0, 0, 24.0, 23.0, 25.0, 24.5])
+    assert sorted(got[:4]) == [4, 5, 6, 7] and got[4:] == [-1] * 4 and got[2] == 6   # the slowest rank gets the fastest relay
+    assert plan_relays(all_busy, need, relay_gbs=[0, 0, 0, 0, 15.0, 15.0, 15.0, 15.0]) == [-1] * 8   # cannot carry two streams
+    assert plan_relays([24.0] * 8, need) == [-1] * 8            # uniform and fast: nothing to do
+    assert plan_relays([7.8] * 8, need) == [-1] * 8             # uniformly slow: nobody can help
+    assert plan_relays([8.0, 30.0], need) == [1, -1]
