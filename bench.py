@@ -526,8 +526,14 @@ def main():
             relay_of = plan_relays(worst, needed, relay_gbs=[min(a, b) for a, b in link_fast_only])
         if os.environ.get("RCED_BENCH_FORCE_RELAY"):      # experiment: "4,5,6,7,-1,-1,-1,-1"
             relay_of = [int(x) for x in os.environ["RCED_BENCH_FORCE_RELAY"].split(",")]
-        if relay_of[rank] >= 0:
-            eng.host_set_relay(relay_of[rank])           # ranks are local GPU indices on one node
+        mine = relay_of[rank]
+        if mine >= 0:
+            try:
+                eng.host_set_relay(mine)                 # ranks are local GPU indices on one node
+            except _lib.RcedError as exc:                # e.g. the two GPUs are not peers: copy directly
+                sys.stderr.write("rank %d: no relay through GPU %d (%s)\n" % (rank, mine, exc))
+                mine = -1
+        relay_of = [int(x) for x in per_rank(mine)]      # what every rank really does
         barrier()
 
     # measured FP32 FFMA peak of this GPU (the roofline denominator; MEASURED_PEAKS.json has none)
