@@ -616,7 +616,10 @@ int rced_istft(rced_handle* h, const float* pred, const float* phase, const int6
     p.row_off = reinterpret_cast<const long long*>(row_off);
     p.n_utt = n_utt;
     p.irfft_n = irfft_n;
+    // 128-sample segments per CTA: 64 in large launches; small launches (one utterance, a streaming block) take 16 so
+    // that more CTAs share the work (every CTA replays 8 segments to rebuild the de-emphasis carry)
     long long chunk = 64;
+    if ((long long)n_utt * ((max_rows_per_utt + 1 + 63) / 64) < 148) chunk = 16;
     while ((max_rows_per_utt + 1 + chunk - 1) / chunk > 65535) chunk *= 2;
     p.chunk_segs = (int)chunk;
     p.out = out;

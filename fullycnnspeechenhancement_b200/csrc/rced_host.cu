@@ -158,9 +158,13 @@ static cudaError_t ensure(T*& p, size_t& cap, size_t need) {
 }
 
 // one chunk [c0, c1) of the call through buffer set b
+// `inline_copies`: a synchronous call that is a single chunk (one utterance, a streaming block) puts its copies on the
+// compute stream as well -- nothing could overlap them, and every hand-over between streams costs a few microseconds
 static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* wav, const int64_t* wav_off, const int32_t* wav_len,
-                     int c0, int c1, int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len) {
+                     int c0, int c1, int irfft_n, float* out, const int64_t* out_off, const int32_t* out_len, bool inline_copies = false) {
     const int n = c1 - c0;
+    const cudaStream_t s_in = inline_copies ? pipe->s_compute : pipe->s_in;
+    const cudaStream_t s_out = inline_copies ? pipe->s_compute : pipe->s_out;
     // sample ranges of the chunk in the caller's buffers, frame counts
     int64_t in_lo = INT64_MAX, in_hi = 0, o_lo = INT64_MAX, o_hi = 0, rows = 0, max_rows = 0;
     bool out_contiguous = true;
@@ -234,9 +238,9 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
     // ---- copy-in: behind the kernels that read this set's previous waveforms and tables
     // development aid (tools/e2e_sweep.py): RCED_HOST_NOCOPY=1 leaves the waveform copies out to see what they cost
     static const bool no_copy = getenv("RCED_HOST_NOCOPY") != nullptr;
-    const bool relay = pipe->relay >= 0 && !pipe->recomputing;
+    const bool relay = pipe->relay >= 0 && !pipe->recomputing && !inline_copies;
     const size_t in_bytes = (size_t)(in_hi - in_lo) * sizeof(float), out_bytes = (size_t)(o_hi - o_lo) * sizeof(float);
-    cudaStreamWaitEvent(pipe->s_in, b.computed, 0);
+    cudaStreamWaitEvent(s_in, b.computed, 0);
     if (relay && !no_copy) {
         // host -> relay device (its link to the host) -> this device (NVLink), on the relay's copy-in stream
         cudaSetDevice(pipe->relay);
@@ -262,10 +266,10 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
         cudaSetDevice(h->device);
         if (e != cudaSuccess) return cuda_fail(e, "host pipeline: H2D waveforms through the relay device");
     } else if (!no_copy &&
-        (e = cudaMemcpyAsync(b.d_wav, wav + in_lo, in_bytes, cudaMemcpyHostToDevice, pipe->s_in)) != cudaSuccess)
+        (e = cudaMemcpyAsync(b.d_wav, wav + in_lo, in_bytes, cudaMemcpyHostToDevice, s_in)) != cudaSuccess)
         return cuda_fail(e, "host pipeline: H2D waveforms");
-    if ((e = cudaMemcpyAsync(dm, hm, meta_bytes, cudaMemcpyHostToDevice, pipe->s_in)) != cudaSuccess) return cuda_fail(e, "host pipeline: H2D tables");
-    cudaEventRecord(b.uploaded, pipe->s_in);
+    if ((e = cudaMemcpyAsync(dm, hm, meta_bytes, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "host pipeline: H2D tables");
+    cudaEventRecord(b.uploaded, s_in);
 
     // ---- compute: behind the upload, and behind the download of what this set's d_out held before
     const int64_t* d_wav_off = reinterpret_cast<const int64_t*>(dm + o_wav_off);
@@ -289,9 +293,9 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
     cudaEventRecord(b.computed, pipe->s_compute);
 
     // ---- copy-out
-    cudaStreamWaitEvent(pipe->s_out, b.computed, 0);
+    cudaStreamWaitEvent(s_out, b.computed, 0);
     if (d_flags) {   // tensor-core launch: its guard words travel to the host, the chunk is remembered
-        e = cudaMemcpyAsync(pipe->h_flags + 2 * pipe->pending.size(), d_flags, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, pipe->s_out);
+        e = cudaMemcpyAsync(pipe->h_flags + 2 * pipe->pending.size(), d_flags, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s_out);
         if (e != cudaSuccess) return cuda_fail(e, "host pipeline: D2H guard words");
         pipe->pending.push_back(PendingChunk{wav, wav_off, wav_len, c0, c1, irfft_n, out, out_off, out_len});
     }
@@ -306,12 +310,12 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
         if (e == cudaSuccess) e = cudaEventRecord(b.r_downloaded, pipe->r_out);
         cudaSetDevice(h->device);
     } else if (out_contiguous) {
-        e = cudaMemcpyAsync(out + o_lo, b.d_out, out_bytes, cudaMemcpyDeviceToHost, pipe->s_out);
+        e = cudaMemcpyAsync(out + o_lo, b.d_out, out_bytes, cudaMemcpyDeviceToHost, s_out);
     } else {   // gaps between the outputs belong to the caller: copy utterance by utterance
         for (int u = c0; u < c1 && e == cudaSuccess; ++u)
-            e = cudaMemcpyAsync(out + out_off[u], b.d_out + (out_off[u] - o_lo), (size_t)out_len[u] * sizeof(float), cudaMemcpyDeviceToHost, pipe->s_out);
+            e = cudaMemcpyAsync(out + out_off[u], b.d_out + (out_off[u] - o_lo), (size_t)out_len[u] * sizeof(float), cudaMemcpyDeviceToHost, s_out);
     }
-    cudaEventRecord(b.downloaded, pipe->s_out);
+    cudaEventRecord(b.downloaded, s_out);
     return e == cudaSuccess ? RCED_OK : cuda_fail(e, "host pipeline: D2H waveforms");
 }
 
@@ -387,7 +391,8 @@ static int enhance_host_impl(rced_handle* h, const float* wav, const int64_t* wa
             if (rc != RCED_OK) return rc;
         }
         BufferSet& b = p->set[p->next_set++ % (unsigned int)kSets];
-        rc = run_chunk(h, p, b, wav, wav_off, wav_len, bounds[i], bounds[i + 1], irfft_n, out, out_off, out_len);
+        rc = run_chunk(h, p, b, wav, wav_off, wav_len, bounds[i], bounds[i + 1], irfft_n, out, out_off, out_len,
+                       !async && bounds.size() == 2);
         if (rc != RCED_OK) return rc;
     }
     return RCED_OK;

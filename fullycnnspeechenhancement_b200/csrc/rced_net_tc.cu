@@ -41,6 +41,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -389,6 +390,10 @@ struct TcParams {
     int n_slots;
     unsigned int* flags;         // [0] bits of the largest |activation| stored as FP16 (scaled domain; >= inf: an input was not finite), [1] protocol error
     long long* trace;            // development aid (RCED_TC_TRACE): clock64 stamps of CTA 0's second batch, or null
+    // Launch shape: frames per CTA batch (kFB, or fewer when the launch is too small to give every SM a full batch: the
+    // latency of one utterance or of a streaming block is the time of ONE batch, which shrinks with its row tiles) and the
+    // row tiles that hold them (ceil(fb * 136 / 128)); uniform over the launch, so the (step, tile) sequence stays regular
+    int fb, nt;
 };
 // trace slots: [step][tile][event]; events: 0 MMA issue begins, 1 MMA issued (commit), 2 epilogue
 // past its waits, 3 accumulator in registers, 4 epilogue done (arrive); tile 0 only: 5 / 6 before /
@@ -424,7 +429,7 @@ struct Ctx {
     unsigned int* err;
     long long* trace;
     bool tracing;
-    int lane, quad, grp, et, nf;
+    int lane, quad, grp, et, nf, nt;
     float* skip;
     float* outp;        // [2][kRows]: the two partial sums of every output row of the (1,129) layer
     long long g0;
@@ -498,10 +503,10 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
     // MMAs of both neighbour tiles.  The tiles are issued by different threads, each committing in its
     // own order, so all three commits are waited for.
 #ifdef RCED_TC_DIAG_WAIT2   // diagnosis only (unsafe): without the commit of the tile before
-    mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t - 1)),
+    mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < c.nt ? t + 1 : t - 1)),
                bar_addr(c, kBarAccFull + t), par, c.err, 100 + s);
 #else
-    mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t)),
+    mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < c.nt ? t + 1 : t)),
                bar_addr(c, kBarAccFull + (t > 0 ? t - 1 : t)), par, c.err, 100 + s);
 #endif
     fence_after();
@@ -654,7 +659,7 @@ __device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const 
     constexpr int s = num_layers(ARCH) - 1;
 #if RCED_TC_BOUNDARY
     if (nx.nf > 0)
-        mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < kTiles ? t + 1 : t)),
+        mbar_wait3(bar_addr(c, kBarAccFull + t), bar_addr(c, kBarAccFull + (t + 1 < c.nt ? t + 1 : t)),
                    bar_addr(c, kBarAccFull + (t > 0 ? t - 1 : t)), par, c.err, 300);
     else
 #endif
@@ -670,7 +675,7 @@ __device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const 
     const bool vb = rb >= 0 && fb < c.nf && rb - fb * kFS < kBins;
 #pragma unroll 1
     for (int odd = 0; odd < 2; ++odd) {
-        if (odd && (t == 0 || t == kTiles - 1)) break;   // no odd frame reaches the first or the last row tile
+        if (odd && (t == 0 || (c.nt == kTiles && t == kTiles - 1))) break;   // no odd frame reaches the first row tile, nor the last one of a full batch
         float v[kFinalN];
 #pragma unroll
         for (int g = 0; g < kFinalN / 8; ++g) {
@@ -796,7 +801,8 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
     __syncthreads();
     fence_after();
     const uint32_t tm = s_tmem;
-    const long long NB = (p.total_rows + kFB - 1) / kFB;
+    const int FB = p.fb, NT = p.nt;   // frames and row tiles per batch of this launch
+    const long long NB = (p.total_rows + FB - 1) / FB;
 
     if (warp == 0 || warp == 3 || (warp >= 5 && warp < kCtrlWarps)) {
         // ================= MMA issue =================
@@ -832,14 +838,14 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                     // buffers and n_steps is even, so step s always uses buffer s & 1
                     const uint32_t tile16 = (uint32_t)c_issue<ARCH>.tile16[s];
                     const uint32_t ub0 = ((w16_0 + (uint32_t)(s & 1) * w16_step) & 0x3FFFu) | ((uint32_t)c_issue<ARCH>.rows[s] << 16);
-                    const int t_first = (iss + kIssuers - (int)((k * kTiles) % kIssuers)) % kIssuers;
+                    const int t_first = (iss + kIssuers - (int)((k * (uint32_t)NT) % kIssuers)) % kIssuers;
 #pragma unroll 1
-                    for (int t = t_first; t < kTiles; t += kIssuers) {
+                    for (int t = t_first; t < NT; t += kIssuers) {
                         // the scout (warp 2) has waited on this tile's mbarriers and published its index: a
                         // shared-memory load costs ~30 cycles where an mbarrier test costs ~160 (umma_probe
                         // lat), and it is only needed when the last value seen does not cover this tile
                         stamp(p.trace, tr, s, t, 5);
-                        const uint32_t need = k * kTiles + t + 1;
+                        const uint32_t need = k * (uint32_t)NT + t + 1;
                         for (int spin = 0; seen < need; ++spin) {
                             seen = ld_acquire(flag);
                             if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
@@ -852,7 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                         // once entered).  Holding one thread back -- prepared, dependency cleared -- keeps the
                         // finish times staggered.
                         {
-                            const uint32_t gidx = k * kTiles + t;   // global tile index
+                            const uint32_t gidx = k * (uint32_t)NT + t;   // global tile index
                             if (gidx >= (uint32_t)RCED_TC_MAXINFLIGHT) {
                                 const uint32_t want = gidx - (uint32_t)RCED_TC_MAXINFLIGHT + 1u;
                                 for (int spin = 0; issued_seen < want; ++spin) {
@@ -879,7 +885,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                             // further, 32 accumulator columns each) five row-shifted blocks of three products
 #pragma unroll 1
                             for (int odd = 0; odd < 2; ++odd) {
-                                if (odd && (t == 0 || t == kTiles - 1)) break;   // no odd frame reaches these row tiles
+                                if (odd && (t == 0 || (NT == kTiles && t == kTiles - 1))) break;   // no odd frame reaches these row tiles
                                 const uint32_t dd = d + (uint32_t)(odd * kFinalN);
                                 const uint32_t po = toff + (uint32_t)(odd * 2 * kPlane16);
 #pragma unroll
@@ -943,17 +949,17 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 // buffer itn & 1 was read by the staging of batch itn - 2: wait until the scout has cleared every row
                 // tile of that batch's first layer (the staging of its last tile has then been released; round-1 form:
                 // its counter has passed the input barrier, i.e. the batch's first tile)
-                const uint32_t need = (itn - 2) * NS * kTiles + (RCED_TC_BOUNDARY ? kTiles : 1);
+                const uint32_t need = (itn - 2) * NS * (uint32_t)NT + (RCED_TC_BOUNDARY ? (uint32_t)NT : 1u);
                 for (int spin = 0; ld_acquire(flag) < need; ++spin) {
                     __nanosleep(200);
                     if ((spin & 255) == 255 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
                 }
             }
-            const long long g0 = batch * kFB;
+            const long long g0 = batch * FB;
             // per frame of the batch: which of its 8 time taps (rows g-3 .. g+4) lie inside its utterance
             int* tm8 = reinterpret_cast<int*>(bnd) + (itn & 1) * 8;
             int m = 0;
-            if (lane < kFB) {
+            if (lane < FB) {
                 long long lo = 0, hi = 0;
                 const long long g = g0 + lane;
                 if (g < p.total_rows) locate(p.row_off, p.n_utt, g, lo, hi);
@@ -962,7 +968,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                 tm8[lane] = m;
             }
             float* ib = inbuf + (itn & 1) * kInRows * kInStride;
-            for (int j = 0; j < kInRows; ++j) {
+            for (int j = 0; j < FB + 7; ++j) {
                 const long long src = g0 - 3 + j;
                 const bool ok = src >= 0 && src < p.total_rows;
                 uint32_t mb = 0;   // largest |x| of the row as a bit pattern (NaN orders above infinity)
@@ -1016,7 +1022,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                     const uint32_t k = it * NS + s;
                     const int wb = k & 1;
 #pragma unroll 1
-                    for (int t = 0; t < kTiles; ++t) {
+                    for (int t = 0; t < NT; ++t) {
                         if (t == 0) {
                             // first layer: its input is staged (the first batch: by all epilogue warps up front; later
                             // batches with RCED_TC_BOUNDARY: by the output layer's epilogues, covered by act_ready below)
@@ -1025,7 +1031,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                             if (k > 0) mbar_wait(bars + 8 * (kBarActReady + 0), (k - 1) & 1, err, 3);
                         }
                         // (step 0 of a batch: the output layer's epilogues of the batch before have read the accumulators)
-                        if (k > 0 && t + 1 < kTiles) mbar_wait(bars + 8 * (kBarActReady + t + 1), (k - 1) & 1, err, 4);
+                        if (k > 0 && t + 1 < NT) mbar_wait(bars + 8 * (kBarActReady + t + 1), (k - 1) & 1, err, 4);
                         st_release(flag, ++done);
                     }
                 }
@@ -1048,6 +1054,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         c.lane = lane;
         c.quad = warp & 3;
         c.grp = (warp - kCtrlWarps) >> 2;   // four consecutive warps cover the four lane quadrants
+        c.nt = NT;
         c.et = (warp - kCtrlWarps) * 32 + lane;
         c.skip = p.skip + (size_t)s_slot * skip_floats_per_cta(ARCH);
         c.outp = reinterpret_cast<float*>(smem + smem_out_off(ARCH));
@@ -1059,16 +1066,16 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         // Stages the first layer's input of batch sb (local index sit): "channel" = time tap, rows g-3 .. g+4
         // of the utterance, from the block the prefetch warp has loaded.  Plane 0 must be free.
         auto stage_input = [&](const long long sb, const uint32_t sit) {
-            const long long sg0 = sb * kFB;
+            const long long sg0 = sb * FB;
             const long long left = p.total_rows - sg0;
-            const int snf = left < kFB ? (int)left : kFB;
+            const int snf = left < FB ? (int)left : FB;
             for (int spin = 0; ld_acquire(bars + 8 * kNextInSlot) <= sit; ++spin)
                 if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
             const int* tm8 = reinterpret_cast<const int*>(bnd) + (sit & 1) * 8;
             const float* ib = reinterpret_cast<const float*>(smem + smem_in_off(ARCH)) + (sit & 1) * kInRows * kInStride;
             const float* fsc = s_scale + (sit & (kScaleRing - 1)) * 8;
 #pragma unroll 1
-            for (int r = c.et; r < kRows; r += 32 * kEpiWarps) {
+            for (int r = c.et; r < NT * 128; r += 32 * kEpiWarps) {
                 const int fi = r / kFS, b = r - fi * kFS;
                 float v[8];
                 if (fi < snf && b < kBins) {
@@ -1089,9 +1096,9 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
         if ((long long)blockIdx.x < NB) stage_input(blockIdx.x, 0);
         uint32_t it = 0;
         for (long long batch = blockIdx.x; batch < NB; batch += gridDim.x, ++it) {
-            const long long g0 = batch * kFB;
+            const long long g0 = batch * FB;
             const long long left = p.total_rows - g0;
-            c.nf = left < kFB ? (int)left : kFB;
+            c.nf = left < FB ? (int)left : FB;
             c.g0 = g0;
             c.scale = s_scale + (it & (kScaleRing - 1)) * 8;
             c.tracing = p.trace != nullptr && blockIdx.x == 0 && it == 1;
@@ -1100,7 +1107,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             for (int s = 0; s < NL - 1; ++s) {
                 const uint32_t par = (k0 + s) & 1;
 #pragma unroll 1
-                for (int t = c.grp; t < kTiles; t += kGroups) epi_conv_tile(c, s, t, par, amax2);
+                for (int t = c.grp; t < NT; t += kGroups) epi_conv_tile(c, s, t, par, amax2);
             }
             // Output layer.  Between this warp's two row tiles the next batch's input is staged: plane 0 is
             // free as soon as the output layer's MMAs have completed, so the first layer of the next
@@ -1113,23 +1120,23 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
 #if RCED_TC_BOUNDARY
                 if (batch + gridDim.x < NB) {
                     const uint32_t sit = it + 1;
-                    const long long left_n = p.total_rows - (batch + gridDim.x) * kFB;
+                    const long long left_n = p.total_rows - (batch + gridDim.x) * FB;
                     for (int spin = 0; ld_acquire(bars + 8 * kNextInSlot) <= sit; ++spin)   // the prefetch warp has the batch
                         if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(err) != 0u) break;
                     nx.ib = reinterpret_cast<const float*>(smem + smem_in_off(ARCH)) + (sit & 1) * kInRows * kInStride;
                     nx.tm8 = reinterpret_cast<const int*>(bnd) + (sit & 1) * 8;
                     nx.fsc = s_scale + (sit & (kScaleRing - 1)) * 8;
-                    nx.nf = left_n < kFB ? (int)left_n : kFB;
+                    nx.nf = left_n < FB ? (int)left_n : FB;
                 }
-                epi_final_tile<ARCH>(c, c.grp, par, nx, amax2);
+                if (c.grp < NT) epi_final_tile<ARCH>(c, c.grp, par, nx, amax2);
 #else
-                epi_final_tile<ARCH>(c, c.grp, par, nx, amax2);
+                if (c.grp < NT) epi_final_tile<ARCH>(c, c.grp, par, nx, amax2);
                 if (batch + gridDim.x < NB) {
                     mbar_wait(bars + 8 * kBarFinalDone, it & 1, err, 6);
                     stage_input(batch + gridDim.x, it + 1);
                 }
 #endif
-                epi_final_tile<ARCH>(c, c.grp + kGroups, par, nx, amax2);
+                if (c.grp + kGroups < NT) epi_final_tile<ARCH>(c, c.grp + kGroups, par, nx, amax2);
             }
             epi_bar();   // both partial sums of every output row are stored
             for (int i = c.et; i < c.nf * kBins; i += 32 * kEpiWarps) {
@@ -1279,7 +1286,7 @@ static cudaError_t launch_tc_t(const tc::TcParams& p, int num_sms, size_t persis
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    long long ctas = (p.total_rows + tc::kFB - 1) / tc::kFB;
+    long long ctas = (p.total_rows + p.fb - 1) / p.fb;
     if (ctas > num_sms) ctas = num_sms;
     if (ctas < 1) return cudaSuccess;
     cudaLaunchConfig_t cfg = {};
@@ -1321,6 +1328,18 @@ cudaError_t launch_net_tc(int arch, const NetParams& np, const unsigned char* wi
     p.n_slots = n_slots;
     p.flags = flags;
     p.trace = trace;
+    // launch shape: full batches of kFB frames when every SM gets at least two of them; smaller launches spread their
+    // frames over the SMs (fb = ceil(rows / SMs)), RCED_TC_FB overrides (experiments)
+    static const int fb_env = getenv("RCED_TC_FB") ? atoi(getenv("RCED_TC_FB")) : 0;
+    int fb = tc::kFB;
+    if (np.total_rows < 2LL * tc::kFB * num_sms) {
+        fb = (int)((np.total_rows + num_sms - 1) / num_sms);
+        if (fb < 1) fb = 1;
+        if (fb > tc::kFB) fb = tc::kFB;
+    }
+    if (fb_env >= 1 && fb_env <= tc::kFB) fb = fb_env;
+    p.fb = fb;
+    p.nt = (fb * tc::kFS + 127) / 128;
     switch (arch) {
         case 1: return launch_tc_t<1>(p, num_sms, persist_bytes, stream);
         case 2: return launch_tc_t<2>(p, num_sms, persist_bytes, stream);

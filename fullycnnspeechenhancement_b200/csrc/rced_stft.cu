@@ -13,14 +13,15 @@
 namespace rced {
 
 constexpr int kStftWarps = 8;
-constexpr int kRowsPerCta = 64;
+constexpr int kRowsPerCta = 64;        // rows a CTA walks in a large launch (tables staged once per 64 rows)
+constexpr int kRowsPerCtaSmall = 8;    // small launches (one utterance, a streaming block): one row per warp, more CTAs
 
 __device__ __forceinline__ long long frames_of(long long L) {   // audio_feature.py:67-70
     const long long d = L >= 256 ? L - 256 : 256 - L;
     return (d + 127) / 128 + 1;
 }
 
-__global__ void __launch_bounds__(kStftWarps * 32) rced_stft_kernel(const StftParams p) {
+__global__ void __launch_bounds__(kStftWarps * 32) rced_stft_kernel(const StftParams p, const int rows_per_cta) {
     __shared__ float2 s_tw[256];
     __shared__ float s_ham[256];
     __shared__ __align__(16) float2 s_z[kStftWarps][kZPad];
@@ -33,8 +34,8 @@ __global__ void __launch_bounds__(kStftWarps * 32) rced_stft_kernel(const StftPa
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const long long g0 = (long long)blockIdx.x * kRowsPerCta;
-    long long g1 = g0 + kRowsPerCta;
+    const long long g0 = (long long)blockIdx.x * rows_per_cta;
+    long long g1 = g0 + rows_per_cta;
     if (g1 > p.total_rows) g1 = p.total_rows;
 
     // utterance of the first row by binary search; later rows walk forward
@@ -142,8 +143,10 @@ cudaError_t upload_tables_stft() { return upload_tables_local(); }
 
 cudaError_t launch_stft(const StftParams& p, cudaStream_t stream) {
     if (p.total_rows <= 0) return cudaSuccess;
-    const long long ctas = (p.total_rows + kRowsPerCta - 1) / kRowsPerCta;
-    rced_stft_kernel<<<(unsigned)ctas, kStftWarps * 32, 0, stream>>>(p);
+    // latency of a small launch is the rows one warp walks: spread them when the GPU would not be full anyway
+    const int rows_per_cta = p.total_rows < 148LL * 2 * kRowsPerCta ? kRowsPerCtaSmall : kRowsPerCta;
+    const long long ctas = (p.total_rows + rows_per_cta - 1) / rows_per_cta;
+    rced_stft_kernel<<<(unsigned)ctas, kStftWarps * 32, 0, stream>>>(p, rows_per_cta);
     count_launch();
     return cudaGetLastError();
 }
