@@ -213,7 +213,7 @@ def ncu_figures(name, sources):
 
 def tc_issue_model(rows):
     """Tensor-core work the K2-TC kernel issues from the library's own step table: per 128-row tile
-    and unit (two (tap, 8-channel) chunks, K = 16) A_hi x [Whi|Wlo'] (N = 2 NP) and A_lo' x Whi (N = NP); 8 tiles per
+    and unit (two (tap, 8-channel) chunks, K = 16) A_hi x [Whi|Wlo'] (N = 2 NP) and A_lo' x Whi (N = NP rounded up to 16); 8 tiles per
     7-frame batch; output layer: 5 row-shifted blocks x 3 products for 14 of the 16 (tile, parity) pairs."""
     import ctypes as ct
     from fullycnnspeechenhancement_b200 import _lib
@@ -227,8 +227,9 @@ def tc_issue_model(rows):
             mac_tile += 1.75 * units * 3 * 128 * npad * 16
             cyc_tile += 1.75 * units * 3 * (32 + npad / 4.0)
         else:
-            mac_tile += units * 128 * 16 * 3 * npad
-            cyc_tile += units * ((32 + 2 * npad / 4.0) + (32 + npad / 4.0))
+            n2 = (npad + 15) // 16 * 16          # N of the second instruction (A_lo' x Whi)
+            mac_tile += units * 128 * 16 * (2 * npad + n2)
+            cyc_tile += units * ((32 + 2 * npad / 4.0) + (32 + n2 / 4.0))
     batches = (rows + 6) // 7
     return 2.0 * mac_tile * 8 * batches, cyc_tile * 8, batches
 

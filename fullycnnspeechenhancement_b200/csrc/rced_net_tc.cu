@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                     const int wb = k & 1;
                     const int nu = c_issue<ARCH>.nu[s], np = c_issue<ARCH>.np[s];
                     const bool fin = s == NL - 1;
-                    const uint32_t id_a = idesc_f16(fin ? np : 2 * np), id_b = idesc_f16(np);
+                    const uint32_t id_a = idesc_f16(fin ? np : 2 * np), id_b = idesc_f16((np + 15) & ~15);   // (N of the second instruction: rced_tc.cuh)
                     const int* ta = c_issue<ARCH>.a + s * kTabStride;
                     // B descriptor of unit 0 (unit u is tile16 * u further): steps alternate between the two weight
                     // buffers and n_steps is even, so step s always uses buffer s & 1

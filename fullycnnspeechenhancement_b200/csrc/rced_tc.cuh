@@ -82,9 +82,16 @@ static_assert(kFS - kBins >= 6 && kLead >= 6, "zero rows must cover the widest S
 RCED_HD constexpr int n_steps(int arch) { return num_layers(arch); }
 RCED_HD constexpr bool is_final(int arch, int s) { return s >= num_layers(arch) - 1; }
 RCED_HD constexpr int step_layer(int arch, int s) { return is_final(arch, s) ? num_layers(arch) - 1 : s; }
+// NP: output channels of a conv step padded to a multiple of 8.  The first instruction of a unit (N = 2 NP, a multiple
+// of 16 as M = 128 requires) writes [hi*Whi | hi*Wlo'] to columns [0, 2 NP); the second one has N = NP rounded up to 16
+// and starts at column NP: when NP is 8 or 24 its last 8 columns hold products with the first rows of the Wlo' block --
+// they land beyond column 2 NP, inside the tile's 64 columns, and are never read.  (Round 1 padded to 16 / 32: the B
+// fetch of a 19..24-channel step cost 32 + 16 rows instead of 24 + 16.)
 RCED_HD constexpr int step_np(int arch, int s) {
-    return is_final(arch, s) ? kFinalN : (spec(arch, s).cout <= 16 ? 16 : 32);
+    return is_final(arch, s) ? kFinalN : (spec(arch, s).cout + 7) / 8 * 8;
 }
+RCED_HD constexpr int step_n2(int arch, int s) { return (step_np(arch, s) + 15) / 16 * 16; }   // N of the second instruction
+static_assert(step_np(1, 4) + step_n2(1, 4) <= kAccCols && step_np(3, 1) + step_n2(3, 1) <= kAccCols, "accumulator columns per tile");
 RCED_HD constexpr int step_groups(int arch, int s) {
     return is_final(arch, s) ? (spec(arch, num_layers(arch) - 1).cin + 7) / 8 : (cin_eff(arch, s) + 7) / 8;
 }
