@@ -7,13 +7,16 @@
 // Design (rced_tc.cuh):
 //  * a CTA takes a batch of 7 consecutive spectrogram frames through all layers.  The (frame, bin)
 //    rows are flattened with a stride of 136 rows per frame, so that the 7 zero rows between two
-//    frames are the SAME-padding halo of both; 8 row tiles of M = 128 cover the batch;
+//    frames are the SAME-padding halo of both; 8 row tiles of M = 128 cover the batch.  (Launches too
+//    small to give every SM two such batches take fewer frames per batch -- TcParams.fb / nt --, so
+//    that the latency of one utterance is the time of a 2- or 3-tile batch, not of an 8-tile one);
 //  * every conv layer is an implicit GEMM without im2col: D[row][cout] += A_tap[row][cin] *
 //    W_tap[cout][cin], one tcgen05.mma (kind::f16, K = 16) per pair of (tap, 8-channel group)
 //    chunks, the A descriptor of a tap being the activation plane shifted by (tap - pad) rows;
 //  * FP32 accuracy from FP16 tensor cores by an error-compensated split: activations and
 //    weights are stored as hi + lo FP16 pairs and every K step issues A_hi x [Whi | Wlo]
-//    (N = 2 NP) and A_lo x Whi (N = NP) into FP32 accumulators in tensor memory.  The residuals are
+//    (N = 2 NP) and A_lo x Whi (N = NP) into FP32 accumulators in tensor memory (two column blocks per
+//    tile: hi*Whi and the two cross products, which carry the residuals' scale).  The residuals are
 //    stored times 2^11, the weights of a step times a power of two and every frame in its own
 //    power-of-two scaled domain (rced_tc.cuh, "Range"), so that the FP16 operands stay in their normal
 //    range for inputs and weights of any magnitude;
@@ -26,15 +29,16 @@
 //    st.shared of the next layer's planes).  Layers overlap tile by tile: the epilogue of (layer,
 //    tile t) starts when the MMAs of tiles t-1, t, t+1 have completed (they read tile t's rows, the
 //    neighbours as halo; planes are updated in place) and the MMAs of (layer+1, t) start when the
-//    epilogues of tiles t-1..t+1 are done;
+//    epilogues of tiles t-1..t+1 are done.  The boundary between two batches is such a layer boundary
+//    too: the output layer's epilogue of row tile t stages the next batch's first-layer rows of tile t;
 //  * the (1,129) output layer runs "taps in N with row-shifted accumulation" (rced_tc.cuh): five MMAs
 //    per row tile whose A descriptors are shifted by -64 .. +64 rows accumulate E[r][n] =
 //    sum_i X[r + 32 (i - 2)] . W[32 i + n] into 32 columns, and the epilogue forms out[b] =
 //    sum_n E[b + n][n] with one shuffle per column (fixed order).  The shifts would reach the
 //    neighbouring frames, so the last conv layer writes an even-frames-only and an odd-frames-only
 //    copy of its output and each parity has its own accumulator columns;
-//  * skip tensors go to a per-CTA FP32 scratch in global memory (L2 resident), written after the
-//    epilogue has released its row tile (the values are read back from the planes);
+//  * skip tensors go to FP32 rows in a region of a global scratch (L2 resident) that the CTA claims
+//    when it starts (rced_slots.cuh: one scratch per handle serves any number of streams);
 //  * range guard: FP16 overflows beyond 65504.  The kernel records the largest |activation| it
 //    stored (in the frames' scaled domains) and whether an input was not finite; rced_forward
 //    re-runs the call with the FP32 FFMA kernel when the guard tripped.

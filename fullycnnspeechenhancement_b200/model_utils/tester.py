@@ -80,9 +80,13 @@ class FullyCNNTester(BaseTester):
         needed).  SDR (GPU energy sums) and STOI (numpy restatement of pystoi) are scored like the
         reference does (tester.py:130-146); PESQ needs the ITU-T P.862 C code, which is not available:
         it is printed as n/a, never as a number."""
+        from concurrent.futures import ThreadPoolExecutor
         Pesq = PESQ(sr=self.sample_rate)
         Stoi = STOI(sr=self.sample_rate)
         eng = self.model.engine()
+        # the reference scores and writes the utterances of a batch in parallel (joblib, tester.py:128-160); here a thread
+        # pool does (numpy's FFTs and the wav writer release the interpreter lock)
+        pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
         for index, (batch_mix, batch_clean, mix_sig, clean_sig) in enumerate(valid_loader):
             start = time.time()
             audio_bins = valid_loader.bins[index]
@@ -93,17 +97,23 @@ class FullyCNNTester(BaseTester):
             lens = [min(len(c), len(d)) for c, d in zip(clean_sig, denoise)]
             scores = sdr_batch([np.asarray(c[:n]) for c, n in zip(clean_sig, lens)], [d[:n] for d, n in zip(denoise, lens)],
                                device=eng.device.index)
-            for i in range(len(audio_bins)):
-                self.sdr_score.update(float(scores[i]))
+            def finish(i):
                 n = lens[i]
-                self.stoi_score.update(float(Stoi(np.asarray(clean_sig[i][:n], dtype=np.float64), denoise[i][:n])))
-                if Pesq.available:
-                    self.pesq_score.update(float(Pesq(np.asarray(clean_sig[i][:n]), denoise[i][:n])))
+                st = float(Stoi(np.asarray(clean_sig[i][:n], dtype=np.float64), denoise[i][:n]))
+                pq = float(Pesq(np.asarray(clean_sig[i][:n]), denoise[i][:n])) if Pesq.available else None
                 name = os.path.basename(valid_loader.dataset.item_name(audio_bins[i]))
                 audio_io.write_wav(os.path.join(self.audio_save_path, name), clean_sig[i], self.sample_rate)
                 audio_io.write_wav(os.path.join(self.audio_save_path, name.replace(".wav", "_mix.wav")), mix_sig[i], self.sample_rate)
                 audio_io.write_wav(os.path.join(self.audio_save_path, name.replace(".wav", "_de.wav")), denoise[i], self.sample_rate)
+                return st, pq
+
+            for i, (st, pq) in enumerate(pool.map(finish, range(len(audio_bins)))):
+                self.sdr_score.update(float(scores[i]))
+                self.stoi_score.update(st)
+                if pq is not None:
+                    self.pesq_score.update(pq)
             print("Testing %d  STOI=%.4f  SDR=%.4f  BatchTime=%.3f" % (index, self.stoi_score.avg, self.sdr_score.avg, time.time() - start))
+        pool.shutdown()
         p_score = "{:.4f}".format(self.pesq_score.avg) if Pesq.available else "n/a (pypesq / ITU-T P.862 not available)"
         print("Average p_score: {}; Average st_score: {:.4f}; Average sd_score: {:.4f}.\n".format(
             p_score, self.stoi_score.avg, self.sdr_score.avg))
