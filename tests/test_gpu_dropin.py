@@ -294,3 +294,23 @@ def test_host_entry_point_through_a_relay_device():
     for a, b, c, d in zip(direct, via, again, back):
         assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
     eng.close()
+
+
+def test_outputs_longer_than_the_noisy_input_follow_rebuild_audio():
+    """FullyCNNTester.test truncates what rebuild_audio produced -- (T+1)*128 samples -- to len(clean_sig[i])
+    (model_utils/tester.py:107-113, utils.py:181-182): a clean signal a little longer than the noisy one gets the samples
+    rebuilt from the zero-padded last frames, not a cut at len(mix)."""
+    from fullycnnspeechenhancement_b200.synth import noisy_utterance
+    from oracle import network, rebuild, stft
+    eng, w = _host_eng(seed=79)
+    waves = [noisy_utterance(40, 1000), noisy_utterance(41, 5000), noisy_utterance(42, 300)]
+    clean_lens = [1010, 5000, 5000]                      # 1010 <= 1024 rebuilt; 5000 <= 5120; 5000 > (2+1)*128 = 384 rebuilt
+    outs = eng.enhance(waves, out_lens=clean_lens)
+    assert [len(o) for o in outs] == [1010, 5000, 384]
+    for wv, o, n in zip(waves, outs, clean_lens):
+        X = stft.compute_spectrogram(wv, 8000, 0.032, 0.016, 256, True).T[None, :, :, None]
+        mag = stft.power_spectrum(X).astype(np.float32)
+        pred = network.forward("FullyCNNV2", w, mag, np.float64).astype(np.float32)
+        ref = rebuild.rebuild_audio([n], pred[..., 0], stft.divide_phase(X)[..., 0], 8000, 32.0, 16.0)[0]
+        assert len(ref) == len(o) and rebuild.sdr_db(ref, o) >= 60.0
+    eng.close()
