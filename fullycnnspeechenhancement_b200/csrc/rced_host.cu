@@ -166,9 +166,11 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
     const cudaStream_t s_in = inline_copies ? pipe->s_compute : pipe->s_in;
     const cudaStream_t s_out = inline_copies ? pipe->s_compute : pipe->s_out;
     // sample ranges of the chunk in the caller's buffers, frame counts
-    int64_t in_lo = INT64_MAX, in_hi = 0, o_lo = INT64_MAX, o_hi = 0, rows = 0, max_rows = 0;
+    int64_t in_lo = INT64_MAX, in_hi = 0, o_lo = INT64_MAX, o_hi = 0, rows = 0, max_rows = 0, sum_in = 0, sum_out = 0;
     bool out_contiguous = true;
     for (int u = c0; u < c1; ++u) {
+        sum_in += wav_len[u];
+        sum_out += out_len[u];
         in_lo = std::min(in_lo, wav_off[u]);
         in_hi = std::max(in_hi, wav_off[u] + wav_len[u]);
         o_lo = std::min(o_lo, out_off[u]);
@@ -179,6 +181,21 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
         const int64_t t = rced_num_frames(wav_len[u]);
         rows += t;
         max_rows = std::max(max_rows, t);
+    }
+    // Utterances that lie close together in the caller's buffers (the normal case: a packed batch) travel as ONE copy
+    // per direction and keep their relative offsets on the device.  Scattered utterances (the span is more than twice
+    // the samples) are copied one by one into a compact device layout, so that the device buffers follow the samples,
+    // not the caller's address span.
+    const bool compact_in = in_hi - in_lo > 2 * sum_in + 4096;
+    const bool compact_out = o_hi - o_lo > 2 * sum_out + 4096;
+    if (compact_in) {
+        in_lo = 0;
+        in_hi = sum_in + 4 * (int64_t)n;   // every utterance starts 16-byte aligned
+    }
+    if (compact_out) {
+        o_lo = 0;
+        o_hi = sum_out + 4 * (int64_t)n;
+        out_contiguous = false;
     }
     // tables: wav_off[n] | row_off[n+1] | out_off[n] (int64), wav_len[n] | out_len[n] (int32)
     const size_t o_wav_off = 0, o_row_off = o_wav_off + 8 * (size_t)n, o_out_off = o_row_off + 8 * (size_t)(n + 1);
@@ -223,11 +240,13 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
     int64_t* m_out_off = reinterpret_cast<int64_t*>(hm + o_out_off);
     int32_t* m_wav_len = reinterpret_cast<int32_t*>(hm + o_wav_len);
     int32_t* m_out_len = reinterpret_cast<int32_t*>(hm + o_out_len);
-    int64_t r = 0;
+    int64_t r = 0, pos_in = 0, pos_out = 0;
     for (int i = 0; i < n; ++i) {
         const int u = c0 + i;
-        m_wav_off[i] = wav_off[u] - in_lo;
-        m_out_off[i] = out_off[u] - o_lo;
+        m_wav_off[i] = compact_in ? pos_in : wav_off[u] - in_lo;
+        m_out_off[i] = compact_out ? pos_out : out_off[u] - o_lo;
+        pos_in += (wav_len[u] + 3) / 4 * 4;
+        pos_out += (out_len[u] + 3) / 4 * 4;
         m_wav_len[i] = wav_len[u];
         m_out_len[i] = out_len[u];
         m_row_off[i] = r;
@@ -238,7 +257,7 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
     // ---- copy-in: behind the kernels that read this set's previous waveforms and tables
     // development aid (tools/e2e_sweep.py): RCED_HOST_NOCOPY=1 leaves the waveform copies out to see what they cost
     static const bool no_copy = getenv("RCED_HOST_NOCOPY") != nullptr;
-    const bool relay = pipe->relay >= 0 && !pipe->recomputing && !inline_copies;
+    const bool relay = pipe->relay >= 0 && !pipe->recomputing && !inline_copies && !compact_in && !compact_out;
     const size_t in_bytes = (size_t)(in_hi - in_lo) * sizeof(float), out_bytes = (size_t)(o_hi - o_lo) * sizeof(float);
     cudaStreamWaitEvent(s_in, b.computed, 0);
     if (relay && !no_copy) {
@@ -265,6 +284,11 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
         if (e == cudaSuccess) e = cudaEventRecord(b.r_uploaded, pipe->r_in);
         cudaSetDevice(h->device);
         if (e != cudaSuccess) return cuda_fail(e, "host pipeline: H2D waveforms through the relay device");
+    } else if (!no_copy && compact_in) {
+        e = cudaSuccess;
+        for (int i = 0; i < n && e == cudaSuccess; ++i)
+            e = cudaMemcpyAsync(b.d_wav + m_wav_off[i], wav + wav_off[c0 + i], (size_t)wav_len[c0 + i] * sizeof(float), cudaMemcpyHostToDevice, s_in);
+        if (e != cudaSuccess) return cuda_fail(e, "host pipeline: H2D waveforms");
     } else if (!no_copy &&
         (e = cudaMemcpyAsync(b.d_wav, wav + in_lo, in_bytes, cudaMemcpyHostToDevice, s_in)) != cudaSuccess)
         return cuda_fail(e, "host pipeline: H2D waveforms");
@@ -313,7 +337,7 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
         e = cudaMemcpyAsync(out + o_lo, b.d_out, out_bytes, cudaMemcpyDeviceToHost, s_out);
     } else {   // gaps between the outputs belong to the caller: copy utterance by utterance
         for (int u = c0; u < c1 && e == cudaSuccess; ++u)
-            e = cudaMemcpyAsync(out + out_off[u], b.d_out + (out_off[u] - o_lo), (size_t)out_len[u] * sizeof(float), cudaMemcpyDeviceToHost, s_out);
+            e = cudaMemcpyAsync(out + out_off[u], b.d_out + m_out_off[u - c0], (size_t)out_len[u] * sizeof(float), cudaMemcpyDeviceToHost, s_out);
     }
     cudaEventRecord(b.downloaded, s_out);
     return e == cudaSuccess ? RCED_OK : cuda_fail(e, "host pipeline: D2H waveforms");

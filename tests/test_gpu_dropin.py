@@ -314,3 +314,40 @@ def test_outputs_longer_than_the_noisy_input_follow_rebuild_audio():
         ref = rebuild.rebuild_audio([n], pred[..., 0], stft.divide_phase(X)[..., 0], 8000, 32.0, 16.0)[0]
         assert len(ref) == len(o) and rebuild.sdr_db(ref, o) >= 60.0
     eng.close()
+
+
+def test_host_entry_point_with_scattered_utterances_and_bad_arguments():
+    """Utterances anywhere in the caller's buffers (any order, large gaps): copied one by one into a compact device layout;
+    nothing outside the outputs is touched.  Argument errors come back as RCED_ERR_ARG, not as CUDA faults."""
+    import ctypes
+    from fullycnnspeechenhancement_b200 import _lib
+    from fullycnnspeechenhancement_b200.synth import noisy_utterance
+    eng, _ = _host_eng(seed=80)
+    waves = [noisy_utterance(60 + i, n) for i, n in enumerate([3000, 1, 777, 4096, 12000])]
+    want = eng.enhance(waves)
+    lens = np.array([len(w) for w in waves], np.int32)
+    off = np.array([900000, 5, 400000, 2000000, 100000], np.int64)          # arbitrary order, gaps of ~10^5..10^6 samples
+    buf = np.zeros(2100000, np.float32)
+    for w, o in zip(waves, off):
+        buf[o:o + len(w)] = w
+    out = np.full(2100000, -3.0, np.float32)
+    t = {"n": len(waves), "wav_off": off, "wav_len": lens, "out_off": off, "out_len": lens}
+    eng.enhance_host(buf, out, t, sync=True)
+    mask = np.ones(len(out), bool)
+    for w, o, r in zip(waves, off, want):
+        assert np.array_equal(out[o:o + len(w)], r)
+        mask[o:o + len(w)] = False
+    assert np.all(out[mask] == -3.0)
+    # argument checks
+    lib, h = _lib.lib(), eng._h
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    bad_len = lens.copy()
+    bad_len[1] = 0
+    assert lib.rced_enhance_host(h, p(buf), p(off), p(bad_len), 5, 512, p(out), p(off), p(lens)) == _lib.ERR_ARG
+    too_long = lens.copy()
+    too_long[2] = 5000                                                          # > (T+1)*128 for a 777-sample utterance
+    assert lib.rced_enhance_host(h, p(buf), p(off), p(lens), 5, 512, p(out), p(off), p(too_long)) == _lib.ERR_ARG
+    assert lib.rced_enhance_host(h, p(buf), p(off), p(lens), 5, 384, p(out), p(off), p(lens)) == _lib.ERR_ARG   # irfft length
+    assert lib.rced_enhance_host(h, p(buf), p(off), p(lens), 0, 512, p(out), p(off), p(lens)) == 0              # nothing to do
+    assert lib.rced_enhance_host(h, None, p(off), p(lens), 5, 512, p(out), p(off), p(lens)) == _lib.ERR_ARG
+    eng.close()
