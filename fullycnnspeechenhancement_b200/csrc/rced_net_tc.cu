@@ -368,6 +368,13 @@ struct IssueTab {
     constexpr IssueTab() : a{}, nu{}, np{}, tile16{}, rows{} {
         for (int s = 0; s < n_steps(ARCH); ++s) {
             nu[s] = step_units(ARCH, s);
+#ifdef RCED_TC_DIAG_PACKEST   // diagnosis only (wrong results): the units a tap-packed partial channel group would save (V2)
+            if (ARCH == 2) {
+                const int cheap[16] = {0, 2, 0, 0, 0, 2, 0, 0, 3, 0, 0, 2, 0, 0, 0, 0};
+                const int more[16] = {0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0, 2, 0};
+                nu[s] -= cheap[s] + (RCED_TC_DIAG_PACKEST > 1 ? more[s] : 0);
+            }
+#endif
             np[s] = step_np(ARCH, s);
             tile16[s] = step_tile_bytes(ARCH, s) >> 4;
             rows[s] = step_tile_rows(ARCH, s);

@@ -15,6 +15,8 @@ VARIANTS=(
   "l1bypass:-DRCED_TC_SKIPHINT=3"
   "validrows:-DRCED_TC_DIAG_VALIDROWS"
   "boundary0:-DRCED_TC_BOUNDARY=0"
+  "packest1_DIAG:-DRCED_TC_DIAG_PACKEST=1"
+  "packest2_DIAG:-DRCED_TC_DIAG_PACKEST=2"
   "skipbulk:-DRCED_TC_SKIP_BULK=1"
   "skipdeferred:-DRCED_TC_SAVE_DEFERRED"
   "noskip_DIAG:-DRCED_TC_DIAG_NOSKIP"
