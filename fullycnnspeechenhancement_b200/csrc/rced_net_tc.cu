@@ -409,8 +409,15 @@ struct TcParams {
 // trace slots: [step][tile][event]; events: 0 MMA issue begins, 1 MMA issued (commit), 2 epilogue
 // past its waits, 3 accumulator in registers, 4 epilogue done (arrive); tile 0 only: 5 / 6 before /
 // after the wait for the step's weights
+// The development trace (RCED_TC_TRACE=<file>, tools/tc_trace_report.py) is compiled in only with -DRCED_TC_TRACING=1:
+// the kernel is sensitive to the size of its hot loops -- the twelve predicated stamps cost 2 % (13.34 -> 13.05 ms).
+#ifndef RCED_TC_TRACING
+#define RCED_TC_TRACING 0
+#endif
 __device__ __forceinline__ void stamp(long long* trace, bool on, int s, int t, int ev) {
+#if RCED_TC_TRACING
     if (on) trace[(s * kTiles + t) * kTraceEvents + ev] = clock64();
+#endif
 }
 
 // what the epilogue of a conv step does, as data: one code body serves every layer (the
@@ -463,6 +470,9 @@ __device__ __forceinline__ void locate(const long long* __restrict__ row_off, in
 // ------------------------------------------------------------------------------------------
 // epilogue of one conv layer for one row tile (runtime-parameterised, see EpiStep)
 // ------------------------------------------------------------------------------------------
+// AFTER: the model adds its skip tensors behind the ReLU (CR-CED V3) instead of in front of it (R-CED V1 / V2); a model has
+// one kind or the other, so the body carries only one of the two forms
+template <bool AFTER>
 __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const int t, const uint32_t par, uint32_t& amax2) {
     EpiStep e = c.epi[s];
 #ifdef RCED_TC_DIAG_NOSKIP   // diagnosis only (wrong results): no skip traffic
@@ -562,14 +572,14 @@ __device__ __forceinline__ void epi_conv_tile(const Ctx& c, const int s, const i
             // hi*Whi + 2^-11 (hi*Wlo' + lo'*Whi) + bias, two channels per instruction
             u64 x = fma2(pack2(d2[2 * i], d2[2 * i + 1]), loinv2, pack2(d1[2 * i], d1[2 * i + 1]));
             x = fma2(pack2(bb[2 * i], bb[2 * i + 1]), sf2, x);
-            if (e.add == 1) x = fma2(pack2(ss[2 * i], ss[2 * i + 1]), r2, x);
+            if (!AFTER && e.add != 0) x = fma2(pack2(ss[2 * i], ss[2 * i + 1]), r2, x);
             float xa, xb;
             unpack2(x, xa, xb);
             if (e.relu) {
                 xa = fmaxf(xa, 0.f);
                 xb = fmaxf(xb, 0.f);
             }
-            if (e.add == 2) {
+            if (AFTER && e.add != 0) {
                 xa = fmaf(ss[2 * i], e.skip_r, xa);
                 xb = fmaf(ss[2 * i + 1], e.skip_r, xb);
             }
@@ -1118,7 +1128,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
             for (int s = 0; s < NL - 1; ++s) {
                 const uint32_t par = (k0 + s) & 1;
 #pragma unroll 1
-                for (int t = c.grp; t < NT; t += kGroups) epi_conv_tile(c, s, t, par, amax2);
+                for (int t = c.grp; t < NT; t += kGroups) epi_conv_tile<ARCH == 3>(c, s, t, par, amax2);
             }
             // Output layer.  Between this warp's two row tiles the next batch's input is staged: plane 0 is
             // free as soon as the output layer's MMAs have completed, so the first layer of the next

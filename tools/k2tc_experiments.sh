@@ -15,6 +15,7 @@ VARIANTS=(
   "l1bypass:-DRCED_TC_SKIPHINT=3"
   "validrows:-DRCED_TC_DIAG_VALIDROWS"
   "boundary0:-DRCED_TC_BOUNDARY=0"
+  "trace:-DRCED_TC_TRACING=1"
   "packest1_DIAG:-DRCED_TC_DIAG_PACKEST=1"
   "packest2_DIAG:-DRCED_TC_DIAG_PACKEST=2"
   "skipbulk:-DRCED_TC_SKIP_BULK=1"
@@ -40,7 +41,7 @@ case "$1" in
       done
     done
     K2TC_PERSIST=1 timeout 60 ./k2v/default 2 persist | tee -a "$out"
-    timeout 60 ./k2v/default 2 trace ../gpurun_out/tc_trace.txt > /dev/null && python tc_trace_report.py ../gpurun_out/tc_trace.txt | grep -E "first_poll|total" >> "$out"
+    timeout 60 ./k2v/trace 2 trace ../gpurun_out/tc_trace.txt > /dev/null && python tc_trace_report.py ../gpurun_out/tc_trace.txt | grep -E "first_poll|total" >> "$out"
     ;;
   *)
     echo "usage: $0 build|run"; exit 2
