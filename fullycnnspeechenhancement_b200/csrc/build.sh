@@ -3,7 +3,8 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
+# RCED_EXTRA_FLAGS: development switches, e.g. RCED_EXTRA_FLAGS=-DRCED_TC_TRACING=1 for the RCED_TC_TRACE clock stamps
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr $RCED_EXTRA_FLAGS"
 mkdir -p build
 pids=()
 for f in rced_net rced_net_tc rced_stft rced_istft rced_api rced_host; do

@@ -567,7 +567,8 @@ int forward_impl(rced_handle* h, const float* mag, const int64_t* row_off, int n
         // development aid: RCED_TC_TRACE=<file> dumps clock64 stamps of CTA 0's second batch (synchronises)
         long long* d_trace = nullptr;
         const int slots = tc_trace_slots(h->arch);
-        if (h->trace_path && cudaMalloc(&d_trace, slots * sizeof(long long)) == cudaSuccess) cudaMemset(d_trace, 0, slots * sizeof(long long));
+        if (h->trace_path && slots > 0 && cudaMalloc(&d_trace, slots * sizeof(long long)) == cudaSuccess)
+            cudaMemset(d_trace, 0, slots * sizeof(long long));   // (slots == 0: built without -DRCED_TC_TRACING=1)
         e = launch_net_tc(h->arch, p, h->d_tc_img, h->d_tc_bias, h->d_tc_skip, h->d_tc_busy, h->num_sms, h->tc_persist_bytes,
                           d_flags, d_trace, h->num_sms, (cudaStream_t)stream);
         count_launch();

@@ -1331,7 +1331,7 @@ static cudaError_t launch_tc_t(const tc::TcParams& p, int num_sms, size_t persis
     return cudaLaunchKernelEx(&cfg, tc::rced_net_tc_kernel<ARCH>, p);
 }
 
-int tc_trace_slots(int arch) { return tc::n_steps(arch) * tc::kTiles * tc::kTraceEvents; }
+int tc_trace_slots(int arch) { return RCED_TC_TRACING ? tc::n_steps(arch) * tc::kTiles * tc::kTraceEvents : 0; }   // 0: trace compiled out
 
 cudaError_t launch_net_tc(int arch, const NetParams& np, const unsigned char* wimg, const float* bias, float* skip,
                           unsigned int* slot_busy, int n_slots, size_t persist_bytes, unsigned int* flags, long long* trace,

@@ -73,7 +73,8 @@ int main(int argc, char** argv) {
     cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dro, ro.data(), ro.size() * 8, cudaMemcpyHostToDevice);
     const int slots = tc_trace_slots(arch);
-    if (trace_path) {
+    if (trace_path && slots == 0) printf("built without -DRCED_TC_TRACING=1: no trace\n");
+    if (trace_path && slots > 0) {
         cudaMalloc(&dtrace, slots * 8);
         cudaMemset(dtrace, 0, slots * 8);
     }
