@@ -747,6 +747,10 @@ __device__ __forceinline__ void epi_final_tile(const Ctx& c, const int t, const 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+#ifndef RCED_TC_UNROLL_UNITS
+#define RCED_TC_UNROLL_UNITS 2   // units per iteration of the issue loop (experiment switch: 1 and 4 measured no better)
+#endif
+constexpr int kUnrollUnits = RCED_TC_UNROLL_UNITS;
 template <int ARCH>
 __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -893,7 +897,7 @@ __global__ void __launch_bounds__(kThreads, 1) rced_net_tc_kernel(const TcParams
                         const uint32_t d = tm + (uint32_t)(t * kAccCols);
                         const uint32_t toff = 128u * t;   // never carries out of the 14-bit start field
                         if (!fin) {
-#pragma unroll 2
+#pragma unroll kUnrollUnits
                             for (int u = 0; u < nu; ++u) {
                                 const uint32_t ua = a16_0 + (uint32_t)ta[u] + toff;
                                 const uint64_t db = make_desc(ub0 + (uint32_t)u * tile16);

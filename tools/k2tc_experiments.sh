@@ -16,6 +16,8 @@ VARIANTS=(
   "validrows:-DRCED_TC_DIAG_VALIDROWS"
   "boundary0:-DRCED_TC_BOUNDARY=0"
   "trace:-DRCED_TC_TRACING=1"
+  "unroll1:-DRCED_TC_UNROLL_UNITS=1"
+  "unroll4:-DRCED_TC_UNROLL_UNITS=4"
   "packest1_DIAG:-DRCED_TC_DIAG_PACKEST=1"
   "packest2_DIAG:-DRCED_TC_DIAG_PACKEST=2"
   "skipbulk:-DRCED_TC_SKIP_BULK=1"
