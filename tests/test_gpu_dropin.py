@@ -351,3 +351,13 @@ def test_host_entry_point_with_scattered_utterances_and_bad_arguments():
     assert lib.rced_enhance_host(h, p(buf), p(off), p(lens), 0, 512, p(out), p(off), p(lens)) == 0              # nothing to do
     assert lib.rced_enhance_host(h, None, p(off), p(lens), 5, 512, p(out), p(off), p(lens)) == _lib.ERR_ARG
     eng.close()
+
+
+def test_host_pipeline_stress_short():
+    """Five seconds of tools/host_stress.py: random batches, chunk sizes and call modes with several calls in flight; every
+    output equals the utterance enhanced alone (FP32 kernel: bit for bit)."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "tools", "host_stress.py"), "5", "ffma"], capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0 and "host stress ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
