@@ -68,10 +68,44 @@ __device__ __forceinline__ float2 shfl_xor2(float2 a, int m) {
     return make_float2(__shfl_xor_sync(0xffffffffu, a.x, m), __shfl_xor_sync(0xffffffffu, a.y, m));
 }
 
+// The eight twiddles of a transform depend on the lane only.  Read from tw256 itself their indices are strided
+// (2 b lane, (lane & (s - 1)) 128 / s): up to 8 lanes of a half-warp on one bank pair, 62 shared-memory wavefronts
+// per transform where 16 would do.  Each CTA therefore keeps a copy ordered [twiddle][lane] - consecutive lanes,
+// consecutive 8-byte entries: rows 0..2 the twiddles after the radix-4 step (b = 1..3), rows 3..7 the stages
+// s = 16..1.
+constexpr int kLaneTw = 8 * 32;
+__device__ __forceinline__ int lane_tw_index(int row, int lane) {
+    if (row < 3) return 2 * lane * (row + 1);   // <= 186
+    const int s = 16 >> (row - 3);
+    return (lane & (s - 1)) * (128 / s);
+}
+// Rows 3..7 hold the twiddle only for the lanes that multiply by it (lane & s); the others hold 1, so that a stage is
+// the same instructions on every lane: t = o -+ v, v = t * w.
+__device__ __forceinline__ void fill_lane_tw(float2* lane_tw, const float2* tw256) {   // before a __syncthreads()
+    for (int i = threadIdx.x; i < kLaneTw; i += blockDim.x) {
+        const int row = i >> 5, lane = i & 31;
+        const bool one = row >= 3 && (lane & (16 >> (row - 3))) == 0;
+        lane_tw[i] = one ? make_float2(1.f, 0.f) : tw256[lane_tw_index(row, lane)];
+    }
+}
+// a * (s, s) + b as one packed FP32 instruction (FFMA2)
+__device__ __forceinline__ float2 cfma_s(float2 a, float s, float2 b) {
+    unsigned long long pa, ps, pb, pd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ps) : "f"(s));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pd) : "l"(pa), "l"(ps), "l"(pb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(pd));
+    return d;
+}
+// HBM -> L2 prefetch of the line holding p (no register, no scoreboard)
+__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // In : v[a] = z[lane + 32 a]                       (natural order)
 // Out: v[b] = Z[4 * bitrev5(lane) + b]             (INV: unscaled inverse transform)
 template <bool INV>
-__device__ __forceinline__ void fft128_warp(float2 (&v)[4], const int lane, const float2* __restrict__ tw256) {
+__device__ __forceinline__ void fft128_warp(float2 (&v)[4], const int lane, const float2* __restrict__ lane_tw) {
     const float2 s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]);
     const float2 s2 = cadd(v[1], v[3]), s3 = csub(v[1], v[3]);
     // forward: -i*s3 = (s3.y, -s3.x); inverse: +i*s3 = (-s3.y, s3.x)
@@ -82,19 +116,22 @@ __device__ __forceinline__ void fft128_warp(float2 (&v)[4], const int lane, cons
     v[3] = csub(s1, r3);
 #pragma unroll
     for (int b = 1; b < 4; ++b) {
-        float2 w = tw256[2 * lane * b];   // <= 186
+        float2 w = lane_tw[32 * (b - 1) + lane];
         if (INV) w.y = -w.y;
         v[b] = cmul(v[b], w);
     }
+    int row = 3;
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        float2 w = tw256[(lane & (s - 1)) * (128 / s)];
+    for (int s = 16; s >= 1; s >>= 1, ++row) {
+        // lanes with bit s: (o - v) * w; the others: (o + v) * 1 - exactly o + v.  The last stage's twiddle is 1 on
+        // every lane.
+        const float sg = (lane & s) != 0 ? -1.f : 1.f;
+        float2 w = lane_tw[32 * row + lane];
         if (INV) w.y = -w.y;
-        const bool hi = (lane & s) != 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const float2 o = shfl_xor2(v[b], s);
-            v[b] = hi ? cmul(csub(o, v[b]), w) : cadd(v[b], o);
+            const float2 t = cfma_s(v[b], sg, shfl_xor2(v[b], s));
+            v[b] = s > 1 ? cmul(t, w) : t;
         }
     }
 }

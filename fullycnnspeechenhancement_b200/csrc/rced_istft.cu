@@ -30,19 +30,21 @@ struct ScanConsts {
 
 template <bool N512>
 __global__ void __launch_bounds__(kIstftWarps * 32) rced_istft_kernel(const IstftParams p, const ScanConsts sc) {
-    __shared__ float2 s_tw[256];
+    __shared__ float2 s_htw[128];          // W256^{-k} / 2, k < 128
     __shared__ float2 s_tw512[132];
-    __shared__ float s_iham[256];
+    __shared__ __align__(16) float s_iham[256];   // 1 / (hamming * irfft length): the transform's scale folded in (a power of two)
+    __shared__ float2 s_ltw[kLaneTw];
     __shared__ float2 s_y[kIstftWarps][132];
     __shared__ __align__(16) float2 s_ze[kIstftWarps][kZPad];
     __shared__ __align__(16) float2 s_zo[kIstftWarps][kZPad];
     __shared__ float s_wend[2][kIstftWarps];
 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        s_tw[i] = g_tables.tw256[i];
-        s_iham[i] = g_tables.inv_ham[i];
+        if (i < 128) s_htw[i] = make_float2(0.5f * g_tables.tw256[i].x, -0.5f * g_tables.tw256[i].y);
+        s_iham[i] = g_tables.inv_ham[i] * (N512 ? 1.f / 256.f : 1.f / 128.f);
         if (i < 132) s_tw512[i] = g_tables.tw512[i];
     }
+    fill_lane_tw(s_ltw, g_tables.tw256);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -105,28 +107,33 @@ __global__ void __launch_bounds__(kIstftWarps * 32) rced_istft_kernel(const Istf
                     bk = ak;
                     bn = make_float2(-2.f * y128.y, 0.f);
                 }
-                const float2 wc = cconj(s_tw[k]);      // W256^{-k}
+                // Z = E + i O, E = (A_k + conj A_{128-k}) / 2, O = (A_k - conj A_{128-k}) / 2 * W256^{-k}; the halves
+                // are folded into the table (s_htw = W256^{-k} / 2: scaling by 1/2 is exact, same bits)
+                const float2 hw = s_htw[k];
                 {
                     const float2 cn = cconj(an);
-                    const float2 e = make_float2(0.5f * (ak.x + cn.x), 0.5f * (ak.y + cn.y));
-                    const float2 o = cmul(make_float2(0.5f * (ak.x - cn.x), 0.5f * (ak.y - cn.y)), wc);
-                    ze[a] = make_float2(e.x - o.y, e.y + o.x);   // e + i o
+                    const float2 sm = cadd(ak, cn), o = cmul(csub(ak, cn), hw);
+                    ze[a] = make_float2(fmaf(0.5f, sm.x, -o.y), fmaf(0.5f, sm.y, o.x));
                 }
                 if (N512) {
                     const float2 cn = cconj(bn);
-                    const float2 e = make_float2(0.5f * (bk.x + cn.x), 0.5f * (bk.y + cn.y));
-                    const float2 o = cmul(make_float2(0.5f * (bk.x - cn.x), 0.5f * (bk.y - cn.y)), wc);
-                    zo[a] = make_float2(e.x - o.y, e.y + o.x);
+                    const float2 sm = cadd(bk, cn), o = cmul(csub(bk, cn), hw);
+                    zo[a] = make_float2(fmaf(0.5f, sm.x, -o.y), fmaf(0.5f, sm.y, o.x));
                 }
             }
-            fft128_warp<true>(ze, lane, s_tw);
-            if (N512) fft128_warp<true>(zo, lane, s_tw);
-            const int k0 = zpad(4 * bitrev5(lane));   // (a run of four never crosses a padding step)
-            *reinterpret_cast<float4*>(&s_ze[warp][k0]) = make_float4(ze[0].x, ze[0].y, ze[1].x, ze[1].y);
-            *reinterpret_cast<float4*>(&s_ze[warp][k0 + 2]) = make_float4(ze[2].x, ze[2].y, ze[3].x, ze[3].y);
-            if (N512) {
-                *reinterpret_cast<float4*>(&s_zo[warp][k0]) = make_float4(zo[0].x, zo[0].y, zo[1].x, zo[1].y);
-                *reinterpret_cast<float4*>(&s_zo[warp][k0 + 2]) = make_float4(zo[2].x, zo[2].y, zo[3].x, zo[3].y);
+            fft128_warp<true>(ze, lane, s_ltw);
+            if (N512) fft128_warp<true>(zo, lane, s_ltw);
+            // of the 128 outputs only the 32 (irfft_n = 512) or 64 behind this segment are read back: the lanes that
+            // hold them stage them
+            const int br = bitrev5(lane);
+            const int k0 = zpad(4 * br);   // (a run of four never crosses a padding step)
+            if ((N512 ? br >> 3 : br >> 4) == half) {
+                *reinterpret_cast<float4*>(&s_ze[warp][k0]) = make_float4(ze[0].x, ze[0].y, ze[1].x, ze[1].y);
+                *reinterpret_cast<float4*>(&s_ze[warp][k0 + 2]) = make_float4(ze[2].x, ze[2].y, ze[3].x, ze[3].y);
+                if (N512) {
+                    *reinterpret_cast<float4*>(&s_zo[warp][k0]) = make_float4(zo[0].x, zo[0].y, zo[1].x, zo[1].y);
+                    *reinterpret_cast<float4*>(&s_zo[warp][k0 + 2]) = make_float4(zo[2].x, zo[2].y, zo[3].x, zo[3].y);
+                }
             }
             __syncwarp();
             const int m0 = 128 * half + 4 * lane;      // position inside the 256-sample frame
@@ -135,17 +142,15 @@ __global__ void __launch_bounds__(kIstftWarps * 32) rced_istft_kernel(const Istf
                 const int n = 32 * half + lane;
                 const float2 e = s_ze[warp][zpad(n)], o = s_zo[warp][zpad(n)];
                 v = make_float4(e.x, o.x, e.y, o.y);
-                const float sc256 = 1.f / 256.f;
-                v.x *= sc256; v.y *= sc256; v.z *= sc256; v.w *= sc256;
             } else {
                 // y[2n] = Re z[n] / 128, y[2n+1] = Im z[n] / 128
                 const int n = 64 * half + 2 * lane;
                 const float2 e = s_ze[warp][zpad(n)], o = s_ze[warp][zpad(n + 1)];
-                const float sc128 = 1.f / 128.f;
-                v = make_float4(e.x * sc128, e.y * sc128, o.x * sc128, o.y * sc128);
+                v = make_float4(e.x, e.y, o.x, o.y);
             }
-            // de-window (utils.py:128-137)
-            v.x *= s_iham[m0]; v.y *= s_iham[m0 + 1]; v.z *= s_iham[m0 + 2]; v.w *= s_iham[m0 + 3];
+            // scale and de-window (utils.py:128-137)
+            const float4 ih = *reinterpret_cast<const float4*>(s_iham + m0);
+            v.x *= ih.x; v.y *= ih.y; v.z *= ih.z; v.w *= ih.w;
             __syncwarp();
         }
 
@@ -178,10 +183,14 @@ __global__ void __launch_bounds__(kIstftWarps * 32) rced_istft_kernel(const Istf
             const long long s0 = j * 128 + 4 * lane;
             const float o0 = fmaf(sc.a1, cin, p0), o1 = fmaf(sc.a2, cin, p1);
             const float o2 = fmaf(sc.a3, cin, p2), o3 = fmaf(sc.a4, cin, p3);
-            if (s0 + 0 < out_len) out[s0 + 0] = o0;
-            if (s0 + 1 < out_len) out[s0 + 1] = o1;
-            if (s0 + 2 < out_len) out[s0 + 2] = o2;
-            if (s0 + 3 < out_len) out[s0 + 3] = o3;
+            if (s0 + 3 < out_len && ((uintptr_t)(out + s0) & 15) == 0) {
+                *reinterpret_cast<float4*>(out + s0) = make_float4(o0, o1, o2, o3);
+            } else {
+                if (s0 + 0 < out_len) out[s0 + 0] = o0;
+                if (s0 + 1 < out_len) out[s0 + 1] = o1;
+                if (s0 + 2 < out_len) out[s0 + 2] = o2;
+                if (s0 + 3 < out_len) out[s0 + 3] = o3;
+            }
         }
     }
 }

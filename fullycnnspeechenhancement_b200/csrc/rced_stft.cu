@@ -21,15 +21,17 @@ __device__ __forceinline__ long long frames_of(long long L) {   // audio_feature
     return (d + 127) / 128 + 1;
 }
 
-__global__ void __launch_bounds__(kStftWarps * 32) rced_stft_kernel(const StftParams p, const int rows_per_cta) {
-    __shared__ float2 s_tw[256];
+__global__ void __launch_bounds__(kStftWarps * 32, 4) rced_stft_kernel(const StftParams p, const int rows_per_cta) {
+    __shared__ float2 s_htw[128];          // W256^k / 2, k < 128: the split step's twiddles
     __shared__ float s_ham[256];
+    __shared__ float2 s_ltw[kLaneTw];
     __shared__ __align__(16) float2 s_z[kStftWarps][kZPad];
 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        s_tw[i] = g_tables.tw256[i];
+        if (i < 128) s_htw[i] = make_float2(0.5f * g_tables.tw256[i].x, 0.5f * g_tables.tw256[i].y);
         s_ham[i] = g_tables.ham[i];
     }
+    fill_lane_tw(s_ltw, g_tables.tw256);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -69,6 +71,14 @@ __global__ void __launch_bounds__(kStftWarps * 32) rced_stft_kernel(const StftPa
 
         const long long woff = __ldg(p.wav_off + u);
         const float* __restrict__ s = p.wav + woff;
+        // the row this warp transforms next (kStftWarps frames on): its second half is new to the CTA (the first half
+        // is the neighbouring warp's second), 512 bytes = 4 lines; warp 0 has no such neighbour.  Measured on
+        // configs[1]: 0.166 -> 0.160 ms into L2; the same into L1 0.162; the same in K3 gains nothing.
+        if (g + kStftWarps < g1 && g + kStftWarps < hi && 128 * (t + kStftWarps) + 256 <= L) {
+            const float* nx = s + 128 * (t + kStftWarps);
+            if (lane < 4) prefetch_line(nx + 128 + 32 * lane);
+            else if (warp == 0 && lane < 8) prefetch_line(nx + 32 * (lane - 4));
+        }
         float2 v[4];
         if (((woff | (long long)(uintptr_t)p.wav >> 2) & 1) == 0 && 128 * t + 256 <= L) {
             // Frame inside the signal, sample pairs 8-byte aligned: four coalesced 8-byte loads per lane (256
@@ -109,25 +119,28 @@ __global__ void __launch_bounds__(kStftWarps * 32) rced_stft_kernel(const StftPa
                 v[a] = make_float2(e0 * s_ham[2 * n], e1 * s_ham[2 * n + 1]);
             }
         }
-        fft128_warp<false>(v, lane, s_tw);
+        fft128_warp<false>(v, lane, s_ltw);
         const int k0 = zpad(4 * bitrev5(lane));   // (a run of four never crosses a padding step)
         *reinterpret_cast<float4*>(&s_z[warp][k0]) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
         *reinterpret_cast<float4*>(&s_z[warp][k0 + 2]) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
         __syncwarp();
-        // split step: X_k = E_k + W^k O_k from Z_k and Z_{128-k}; |X| and X / |X| with one reciprocal square root
+        // split step: X_k = E_k + W^k O_k from Z_k and Z_{128-k}, E = (Z_k + conj Z_{128-k}) / 2, O = -i (Z_k - conj
+        // Z_{128-k}) / 2, with the halves folded into the table (s_htw = W^k / 2: scaling by 1/2 is exact, so the bits
+        // are those of the unfolded form); |X| and X / |X| with one reciprocal square root (FLT_MIN below it: no
+        // subnormal argument, |X| = 0 stays 0)
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int k = lane + 32 * a;
             const float2 zk = s_z[warp][zpad(k)];
             const float2 zn = cconj(s_z[warp][zpad((128 - k) & 127)]);
-            const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y));
-            const float2 d = csub(zk, zn);
-            const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);   // -i/2 * d
-            const float2 x = cadd(e, cmul(s_tw[k], o));
+            const float2 sm = cadd(zk, zn), d = csub(zk, zn);
+            const float2 h = s_htw[k];
+            const float2 x = make_float2(fmaf(0.5f, sm.x, fmaf(h.x, d.y, h.y * d.x)), fmaf(0.5f, sm.y, fmaf(-h.x, d.x, h.y * d.y)));
             const float m2 = fmaf(x.x, x.x, x.y * x.y);
-            const float inv = rsqrtf(m2);                            // (+inf at 0: not used there)
-            mag[k] = m2 > 0.f ? m2 * inv : 0.f;
-            if (ph) ph[k] = m2 > 0.f ? make_float2(x.x * inv, x.y * inv) : make_float2(1.f, 0.f);
+            float inv;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaxf(m2, 1.17549435e-38f)));
+            mag[k] = m2 * inv;
+            if (ph) ph[k] = make_float2(m2 > 0.f ? x.x * inv : 1.f, x.y * inv);   // exp(j angle(0)) = 1
         }
         if (lane == 0) {   // bin 128 is real: X_128 = Re Z_0 - Im Z_0
             const float2 z0 = s_z[warp][0];

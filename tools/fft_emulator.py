@@ -24,11 +24,14 @@ def fft128_warp(z, inverse=False):
     for b in range(4):
         y[b] = y[b] * tw[(2 * lanes * b) % 256]
     for s in (16, 8, 4, 2, 1):
+        hi = (lanes & s) != 0
+        # the per-lane twiddle table of the kernels: the stage's twiddle on the lanes with bit s, 1 on the others,
+        # so that every lane runs the same two steps t = o -+ v, v = t * w
+        w = np.where(hi, tw[(lanes & (s - 1)) * (128 // s)], 1.0)
+        sg = np.where(hi, -1.0, 1.0)
         for b in range(4):
             o = y[b][lanes ^ s]                                            # shfl_xor
-            hi = (lanes & s) != 0
-            w = tw[(lanes & (s - 1)) * (128 // s)]
-            y[b] = np.where(hi, (o - y[b]) * w, y[b] + o)
+            y[b] = (sg * y[b] + o) * w
     Z = np.zeros(128, complex)
     for l in range(32):
         for b in range(4):
