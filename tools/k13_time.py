@@ -43,5 +43,5 @@ def timed(fn):
 
 k1 = timed(lambda: eng.stft_device(wav, plan["wav_off"], plan["wav_len"], ro, rows, mag, phase))
 k3 = timed(lambda: eng.istft_device(mag, phase, ro, T, out, plan["wav_off"], plan["wav_len"]))
-print("RCED_PREFETCH=%s  K1 median %.4f ms (min %.4f)   K3 median %.4f ms (min %.4f)   checksum %.6e"
-      % (os.environ.get("RCED_PREFETCH", "default"), k1[0], k1[1], k3[0], k3[1], float(out.double().abs().sum())))
+print("K1 median %.4f ms (min %.4f)   K3 median %.4f ms (min %.4f)   checksum %.6e"
+      % (k1[0], k1[1], k3[0], k3[1], float(out.double().abs().sum())))

@@ -139,6 +139,9 @@ def to_json(rep, kernel_substr, out_path, sources):
         v = float(r[ix[name]].replace(",", ""))
         if scale_units:
             u = units[ix[name]].lower()
+            exact = {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}      # times are reported in ms
+            if u in exact:
+                return v * exact[u]
             for pre, m in (("gbyte", 1e9), ("mbyte", 1e6), ("kbyte", 1e3), ("byte", 1.0), ("usecond", 1e-3), ("msecond", 1.0),
                            ("nsecond", 1e-6), ("second", 1e3)):
                 if u.startswith(pre):
