@@ -28,7 +28,7 @@ def run(n):
 
 
 for streams in (3,):   # (copy-in, compute, copy-out: fixed)
-    for rows in ((32768, 131072) if os.environ.get("E2E_QUICK") else (16384, 32768, 65536, 131072, 262144)):
+    for rows in ((32768, 131072) if os.environ.get("E2E_QUICK") else (32768, 65536, 87381, 131072, 180000, 262144)):
         eng.host_config(chunk_rows=rows)
         run(3)
         torch.cuda.synchronize()
