@@ -35,8 +35,11 @@ __global__ void __launch_bounds__(kIstftWarps * 32) rced_istft_kernel(const Istf
     __shared__ __align__(16) float s_iham[256];   // 1 / (hamming * irfft length): the transform's scale folded in (a power of two)
     __shared__ float2 s_ltw[kLaneTw];
     __shared__ float2 s_y[kIstftWarps][132];
-    __shared__ __align__(16) float2 s_ze[kIstftWarps][kZPad];
-    __shared__ __align__(16) float2 s_zo[kIstftWarps][kZPad];
+    __shared__ __align__(16) float2 s_ze[N512 ? 1 : kIstftWarps][kZPad];   // irfft_n = 256: the transform's output, padded
+    // irfft_n = 512: the 32 kept outputs of both transforms, [b][lane's block] with rows of 10 slots: the 8 lanes of a store
+    // write 128 contiguous bytes, the 8 lanes of a quarter-warp load hit slots that differ modulo 8 (no bank conflicts)
+    constexpr int kZzRow = 10;
+    __shared__ __align__(16) float4 s_zz[N512 ? kIstftWarps : 1][4 * kZzRow];
     __shared__ float s_wend[2][kIstftWarps];
 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -89,61 +92,73 @@ __global__ void __launch_bounds__(kIstftWarps * 32) rced_istft_kernel(const Istf
             __syncwarp();
             const float2 y0 = s_y[warp][0], y128 = s_y[warp][128];
             // Hermitian half-spectra A (even output samples) and A' (odd output samples, only for
-            // irfft_n = 512) -> Z_k = E_k + i O_k -> 128-point inverse FFT
-            float2 ze[4], zo[4];
+            // irfft_n = 512) -> Z_k = E_k + i O_k -> 128-point inverse FFT.
+            // Z = E + i O, E = (A_k + conj A_{128-k}) / 2, O = (A_k - conj A_{128-k}) / 2 * W256^{-k}; the halves are
+            // folded into the table (s_htw = W256^{-k} / 2: scaling by 1/2 is exact, same bits)
+            const int m0 = 128 * half + 4 * lane;      // position inside the 256-sample frame
+            const int br = bitrev5(lane);              // the transform leaves lane l with outputs 4 bitrev5(l) + b
+            if (N512) {
+                // the two sequences run as packed pairs from here to the staging buffer: x = (Re Z, Re Z'), y = (Im Z, Im Z')
+                pk2 px[4], py[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int k = lane + 32 * a;           // 0..127
-                const int kn = 128 - k;                // 128..1
-                float2 ak = s_y[warp][k], an = s_y[warp][kn];
-                float2 bk = ak, bn = an;
-                if (N512) {
-                    bk = cmul(ak, s_tw512[k]);
-                    bn = cmul(an, s_tw512[kn]);
+                for (int a = 0; a < 4; ++a) {
+                    const int k = lane + 32 * a;           // 0..127
+                    const int kn = 128 - k;                // 128..1
+                    float2 ak = s_y[warp][k], an = s_y[warp][kn];
+                    float2 bk = cmul(ak, s_tw512[k]), bn = cmul(an, s_tw512[kn]);
+                    if (k == 0) {
+                        ak = make_float2(y0.x, 0.f);
+                        an = make_float2(2.f * y128.x, 0.f);
+                        bk = ak;
+                        bn = make_float2(-2.f * y128.y, 0.f);
+                    }
+                    const float2 hw = s_htw[k];
+                    const pk2 ax = pk_pack(ak.x, bk.x), ay = pk_pack(ak.y, bk.y), nx = pk_pack(an.x, bn.x), ny = pk_pack(an.y, bn.y);
+                    // sm = A_k + conj A_n, d = A_k - conj A_n, o = d * hw, Z = (sm.x / 2 - o.y, sm.y / 2 + o.x)
+                    const pk2 smx = pk_add(ax, nx), smy = pk_sub(ay, ny), dx = pk_sub(ax, nx), dy = pk_add(ay, ny);
+                    const pk2 ox = pk_fma(dx, pk_pack(hw.x, hw.x), pk_mul(dy, pk_pack(-hw.y, -hw.y)));
+                    const pk2 noy = pk_fma(dx, pk_pack(-hw.y, -hw.y), pk_mul(dy, pk_pack(-hw.x, -hw.x)));
+                    px[a] = pk_fma(smx, pk_pack(0.5f, 0.5f), noy);
+                    py[a] = pk_fma(smy, pk_pack(0.5f, 0.5f), ox);
                 }
-                if (k == 0) {
-                    ak = make_float2(y0.x, 0.f);
-                    an = make_float2(N512 ? 2.f * y128.x : y128.x, 0.f);
-                    bk = ak;
-                    bn = make_float2(-2.f * y128.y, 0.f);
+                fft128_warp_pair<true>(px, py, lane, s_ltw);
+                // of the 128 outputs the segment keeps the 32 with index 32 half + lane: the 8 lanes that hold them stage
+                // them as (Re z, Re z', Im z, Im z') = y[4n .. 4n+3] * 256
+                if ((br >> 3) == half) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        float4 q;
+                        pk_unpack(px[b], q.x, q.y);
+                        pk_unpack(py[b], q.z, q.w);
+                        s_zz[warp][kZzRow * b + (br & 7)] = q;
+                    }
                 }
-                // Z = E + i O, E = (A_k + conj A_{128-k}) / 2, O = (A_k - conj A_{128-k}) / 2 * W256^{-k}; the halves
-                // are folded into the table (s_htw = W256^{-k} / 2: scaling by 1/2 is exact, same bits)
-                const float2 hw = s_htw[k];
-                {
+                __syncwarp();
+                v = s_zz[warp][kZzRow * (lane & 3) + (lane >> 2)];
+            } else {
+                float2 ze[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int k = lane + 32 * a;
+                    const int kn = 128 - k;
+                    float2 ak = s_y[warp][k], an = s_y[warp][kn];
+                    if (k == 0) {
+                        ak = make_float2(y0.x, 0.f);
+                        an = make_float2(y128.x, 0.f);
+                    }
+                    const float2 hw = s_htw[k];
                     const float2 cn = cconj(an);
                     const float2 sm = cadd(ak, cn), o = cmul(csub(ak, cn), hw);
                     ze[a] = make_float2(fmaf(0.5f, sm.x, -o.y), fmaf(0.5f, sm.y, o.x));
                 }
-                if (N512) {
-                    const float2 cn = cconj(bn);
-                    const float2 sm = cadd(bk, cn), o = cmul(csub(bk, cn), hw);
-                    zo[a] = make_float2(fmaf(0.5f, sm.x, -o.y), fmaf(0.5f, sm.y, o.x));
+                fft128_warp<true>(ze, lane, s_ltw);
+                // the segment keeps the 64 outputs 64 half + 2 lane (+ 1): y[2n] = Re z[n] / 128, y[2n+1] = Im z[n] / 128
+                const int k0 = zpad(4 * br);   // (a run of four never crosses a padding step)
+                if ((br >> 4) == half) {
+                    *reinterpret_cast<float4*>(&s_ze[warp][k0]) = make_float4(ze[0].x, ze[0].y, ze[1].x, ze[1].y);
+                    *reinterpret_cast<float4*>(&s_ze[warp][k0 + 2]) = make_float4(ze[2].x, ze[2].y, ze[3].x, ze[3].y);
                 }
-            }
-            fft128_warp<true>(ze, lane, s_ltw);
-            if (N512) fft128_warp<true>(zo, lane, s_ltw);
-            // of the 128 outputs only the 32 (irfft_n = 512) or 64 behind this segment are read back: the lanes that
-            // hold them stage them
-            const int br = bitrev5(lane);
-            const int k0 = zpad(4 * br);   // (a run of four never crosses a padding step)
-            if ((N512 ? br >> 3 : br >> 4) == half) {
-                *reinterpret_cast<float4*>(&s_ze[warp][k0]) = make_float4(ze[0].x, ze[0].y, ze[1].x, ze[1].y);
-                *reinterpret_cast<float4*>(&s_ze[warp][k0 + 2]) = make_float4(ze[2].x, ze[2].y, ze[3].x, ze[3].y);
-                if (N512) {
-                    *reinterpret_cast<float4*>(&s_zo[warp][k0]) = make_float4(zo[0].x, zo[0].y, zo[1].x, zo[1].y);
-                    *reinterpret_cast<float4*>(&s_zo[warp][k0 + 2]) = make_float4(zo[2].x, zo[2].y, zo[3].x, zo[3].y);
-                }
-            }
-            __syncwarp();
-            const int m0 = 128 * half + 4 * lane;      // position inside the 256-sample frame
-            if (N512) {
-                // y[4n..4n+3] = (Re ze[n], Re zo[n], Im ze[n], Im zo[n]) / 256
-                const int n = 32 * half + lane;
-                const float2 e = s_ze[warp][zpad(n)], o = s_zo[warp][zpad(n)];
-                v = make_float4(e.x, o.x, e.y, o.y);
-            } else {
-                // y[2n] = Re z[n] / 128, y[2n+1] = Im z[n] / 128
+                __syncwarp();
                 const int n = 64 * half + 2 * lane;
                 const float2 e = s_ze[warp][zpad(n)], o = s_ze[warp][zpad(n + 1)];
                 v = make_float4(e.x, e.y, o.x, o.y);
