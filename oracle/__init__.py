@@ -20,5 +20,13 @@ Parity pinning status:
   anchored only on (a) the published parameter counts 32,765 / 32,192 / 32,653
   (``readme.md:63-67``), (b) agreement between two independently written
   evaluators (a tap-loop NHWC SAME convolution in numpy float64 and
-  ``torch.nn.functional.conv2d`` with explicit asymmetric padding).
+  ``torch.nn.functional.conv2d`` with explicit asymmetric padding), and (c) the
+  reference's OWN model classes (``model_utils/model.py``, imported unmodified by
+  ``oracle/ref_import.load_models``) executed with ``oracle/tf_standin.py`` in place of
+  TensorFlow: the WIRING -- layers, widths, kernel sizes, skip inputs, the position of
+  the addition, the variable scopes -- is then the reference's source, run, not a
+  restatement (``tests/golden/network_ref_model.npz``, agreement 2e-15).  What stays
+  unpinned is the arithmetic of the three TensorFlow operations themselves (SAME
+  padding of the even time kernel, batch-norm epsilon), stated from TensorFlow's
+  documented behaviour in four independently written forms.
 """

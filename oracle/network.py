@@ -12,7 +12,9 @@ TensorFlow-1.14 semantics those call sites imply:
 
 TensorFlow is a third-party dependency that is absent here (pinned
 ``tensorflow-gpu==1.14.0`` in requriements.txt:4), so this file cannot be checked
-against the reference's own execution; see oracle/__init__.py.
+against the reference's own execution under TensorFlow; see oracle/__init__.py.  The wiring IS checked against the
+reference's model classes, executed with oracle/tf_standin.py in place of TensorFlow
+(tests/test_oracle_golden.py::test_network_oracle_matches_the_reference_model_code).
 """
 import numpy as np
 

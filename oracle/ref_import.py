@@ -37,3 +37,18 @@ def load():
     from data_utils.data_loader import DataLoader, AudioParser
     from model_utils.utils import AudioReBuild
     return AudioFeature, AudioReBuild, DataLoader, AudioParser
+
+
+def load_models():
+    """The reference's own model classes {name: class} (model_utils/model.py), imported UNMODIFIED with
+    oracle/tf_standin.py standing in for TensorFlow: `cls(is_training=False)(x)` runs the reference's wiring on the
+    variables given to tf_standin.set_variables()."""
+    if not available():
+        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+    from oracle import tf_standin
+    tf_standin.install()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import importlib
+    model = importlib.import_module("model_utils.model")
+    return {"FullyCNN": model.FullyCNNSEModel, "FullyCNNV2": model.FullyCNNSEModelV2, "FullyCNNV3": model.FullyCNNSEModelV3}

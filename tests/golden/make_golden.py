@@ -13,6 +13,12 @@
   weights.  NOT produced by the reference (TensorFlow 1.14 is not installable):
   parity unpinned, see oracle/__init__.py.  Kept so the GPU box can check the CUDA
   path and the oracle against a value computed elsewhere.
+* ``network_ref_model.npz`` -- outputs of the reference's OWN model classes (model_utils/model.py, imported unmodified)
+  executed with oracle/tf_standin.py in place of TensorFlow, on the inputs and weights of ``network_oracle.npz``, plus the
+  variables each model asks for in creation order.  Pins the wiring (layers, widths, kernel sizes, skip inputs, position of
+  the addition, scopes / checkpoint names) to the reference's source; the arithmetic of conv2d / batch_normalization / relu
+  is the stand-in's restatement of TensorFlow's documented behaviour.  `python tests/golden/make_golden.py network_ref_model`
+  writes only this file.
 """
 import os
 import sys
@@ -26,7 +32,31 @@ from oracle import ref_import, network  # noqa: E402
 from fullycnnspeechenhancement_b200.synth import noisy_utterance  # noqa: E402
 
 
+def make_network_ref_model():
+    from oracle import tf_standin
+    models = ref_import.load_models()
+    net = {}
+    for arch in ("FullyCNN", "FullyCNNV2", "FullyCNNV3"):
+        w = network.random_weights(arch, seed=1234, randomize_bn=True)      # the weights of network_oracle.npz
+        rng = np.random.default_rng(77)
+        for T in (1, 7, 8, 9, 12):
+            x = np.abs(rng.normal(0, 3.0, (2, T, 129, 1))).astype(np.float32)   # the inputs of network_oracle.npz
+            if T not in (1, 8, 12):
+                continue
+            tf_standin.set_variables(w)
+            net["y_%s_%d" % (arch, T)] = models[arch](is_training=False)(x.astype(np.float64))
+            net["xsum_%s_%d" % (arch, T)] = np.array([float(x.astype(np.float64).sum())])
+        req = tf_standin.requested()
+        net["names_" + arch] = np.array([n for n, _ in req])
+        net["shapes_" + arch] = np.array(["x".join(str(d) for d in sh) for _, sh in req])
+    np.savez_compressed(os.path.join(HERE, "network_ref_model.npz"), **net)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "network_ref_model":
+        make_network_ref_model()
+        print("network_ref_model.npz", os.path.getsize(os.path.join(HERE, "network_ref_model.npz")))
+        return
     AudioFeature, AudioReBuild, DataLoader, AudioParser = ref_import.load()
     af = AudioFeature()
 
@@ -87,6 +117,7 @@ def main():
             net["x_%s_%d" % (arch, T)] = x
             net["y_%s_%d" % (arch, T)] = network.forward(arch, w, x, np.float64)
     np.savez_compressed(os.path.join(HERE, "network_oracle.npz"), **net)
+    make_network_ref_model()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

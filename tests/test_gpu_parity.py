@@ -296,3 +296,13 @@ def test_golden_fixtures_on_gpu(dev, engines, golden_dir):
             pred = e.forward_device(t(x.reshape(2 * T, 129)), torch.tensor([0, T, 2 * T], dtype=torch.int64, device=dev))
             torch.cuda.synchronize()
             assert rel_err(pred.cpu().numpy(), y) <= MAG_TOL
+    # the same inputs through the reference's own model classes (tests/golden/make_golden.py, oracle/tf_standin.py)
+    gm = np.load(os.path.join(golden_dir, "network_ref_model.npz"))
+    for arch in ARCHS:
+        e, w = engines[arch]
+        for T in (1, 8, 12):
+            x = n["x_%s_%d" % (arch, T)]
+            y = gm["y_%s_%d" % (arch, T)][..., 0].reshape(2 * T, 129)
+            pred = e.forward_device(t(x.reshape(2 * T, 129)), torch.tensor([0, T, 2 * T], dtype=torch.int64, device=dev))
+            torch.cuda.synchronize()
+            assert rel_err(pred.cpu().numpy(), y) <= MAG_TOL

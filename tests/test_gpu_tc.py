@@ -57,6 +57,25 @@ def _oracle(name, w, mag, row_off):
 
 
 @pytest.mark.parametrize("name", ARCHS)
+def test_tc_matches_the_reference_model_code(name):
+    """The committed outputs of the reference's own model classes (tests/golden/network_ref_model.npz: model_utils/model.py
+    executed with oracle/tf_standin.py in place of TensorFlow) against the tensor-core kernel."""
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gm, n = np.load(os.path.join(gdir, "network_ref_model.npz")), np.load(os.path.join(gdir, "network_oracle.npz"))
+    eng = Enhancer(name, network.random_weights(name, seed=1234, randomize_bn=True), device=0)
+    try:
+        for T in (1, 8, 12):
+            x = n["x_%s_%d" % (name, T)].reshape(2 * T, 129)
+            ref = gm["y_%s_%d" % (name, T)][..., 0].reshape(2 * T, 129)
+            got = _forward(eng, x, [0, T, 2 * T], "tc")
+            assert eng.tc_status()[1] == 0
+            assert rel_err(got, ref) <= 2e-5
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("name", ARCHS)
 def test_tc_forward_matches_oracle_ragged(engines, name):
     eng, w = engines[name]
     rng = np.random.default_rng(17)

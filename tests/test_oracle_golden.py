@@ -114,6 +114,53 @@ def test_network_two_evaluators_and_golden(arch, golden_dir):
         assert np.abs(y - y32).max() / np.abs(y).max() < 1e-5
 
 
+@pytest.mark.parametrize("arch", ["FullyCNN", "FullyCNNV2", "FullyCNNV3"])
+def test_network_oracle_matches_the_reference_model_code(arch, golden_dir):
+    """network_ref_model.npz holds what the reference's OWN model classes (model_utils/model.py, unmodified) compute with
+    oracle/tf_standin.py in place of TensorFlow (tests/golden/make_golden.py): the wiring is the reference's, executed.
+    The oracle must reproduce it, and the variables the reference's code creates must be exactly the ones the weight
+    dicts (oracle.network.random_weights, model_utils/fold.py) carry, with the same shapes."""
+    g = np.load(os.path.join(golden_dir, "network_ref_model.npz"))
+    n = np.load(os.path.join(golden_dir, "network_oracle.npz"))
+    w = network.random_weights(arch, seed=1234, randomize_bn=True)
+    for T in (1, 8, 12):
+        x = n["x_%s_%d" % (arch, T)]
+        assert abs(float(x.astype(np.float64).sum()) - float(g["xsum_%s_%d" % (arch, T)][0])) < 1e-9
+        ref = g["y_%s_%d" % (arch, T)]
+        y = network.forward(arch, w, x, np.float64)
+        assert y.shape == ref.shape
+        assert np.abs(y - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    names, shapes = [str(v) for v in g["names_" + arch]], [str(v) for v in g["shapes_" + arch]]
+    assert sorted(names) == sorted(w.keys())
+    for nm, sh in zip(names, shapes):
+        assert "x".join(str(d) for d in w[nm].shape) == sh, nm
+    # creation order of the conv scopes = the oracle's layer table (the order checkpoints and frozen graphs list them in)
+    scopes = [nm[:-len("/kernel")] for nm in names if nm.endswith("/kernel")]
+    assert scopes == [L["scope"] for L in network.layer_table(arch)]
+    from fullycnnspeechenhancement_b200.model_utils import fold
+    assert sorted(fold.glorot_weights(arch, seed=0).keys()) == sorted(names)
+
+
+@pytest.mark.parametrize("arch", ["FullyCNN", "FullyCNNV2", "FullyCNNV3"])
+def test_reference_model_code_live(arch):
+    """Where /root/reference exists (the authoring container): run the reference's model classes through the stand-in on
+    fresh weights and inputs, ragged T included, against the oracle."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    from oracle import tf_standin
+    cls = ref_import.load_models()[arch]
+    rng = np.random.default_rng(31)
+    for seed, T, bn in ((3, 1, True), (4, 5, True), (5, 16, False)):
+        w = network.random_weights(arch, seed=seed, randomize_bn=bn)
+        x = np.abs(rng.normal(0, 2.0, (3, T, 129, 1)))
+        tf_standin.set_variables(w)
+        ref = cls(is_training=False)(x)
+        y = network.forward(arch, w, x, np.float64)
+        assert np.abs(y - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+        assert len(tf_standin.requested()) == len(w)
+
+
 def test_network_padding_invariance():
     arch = "FullyCNNV3"
     w = network.random_weights(arch, seed=2)
