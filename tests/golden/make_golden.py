@@ -19,6 +19,13 @@
   the addition, scopes / checkpoint names) to the reference's source; the arithmetic of conv2d / batch_normalization / relu
   is the stand-in's restatement of TensorFlow's documented behaviour.  `python tests/golden/make_golden.py network_ref_model`
   writes only this file.
+* ``reference_test_entry.npz`` -- the reference's own evaluation entry point (test.py main(): DataSet, DataLoader,
+  FullyCNNTester with graph creation, checkpoint restore, param_count, the batch loop with rebuild_audio and the scores),
+  UNMODIFIED, run on the small job of tests/golden/ref_entry_case.py with the stand-ins of oracle/ref_import.load_test_entry
+  (TensorFlow: oracle/tf_standin.py; librosa.load / soundfile.write / pystoi / joblib.Parallel: see there): the enhanced
+  waveforms it hands to soundfile.write, its average SDR and STOI and the parameter total it prints, for V1 / V2 / V3;
+  and what infer.py's InferenceEngine(cfg).denoise(file) writes for one of the files.
+  `python tests/golden/make_golden.py reference_test_entry` writes only this file.
 """
 import os
 import sys
@@ -52,7 +59,65 @@ def make_network_ref_model():
     np.savez_compressed(os.path.join(HERE, "network_ref_model.npz"), **net)
 
 
+def make_reference_test_entry():
+    import contextlib
+    import io
+    import tempfile
+    sys.path.insert(0, HERE)
+    import ref_entry_case as case
+    from oracle import tf_standin
+    entry, load_conf = ref_import.load_test_entry()
+
+    RefTester = entry.FullyCNNTester
+
+    class Recording(RefTester):
+        last = None
+
+        def __init__(self, cfg):
+            RefTester.__init__(self, cfg)
+            Recording.last = self
+    entry.FullyCNNTester = Recording
+    out = {}
+    for arch in case.ARCHS:
+        with tempfile.TemporaryDirectory() as d:
+            prefix = os.path.join(d, "ckpt", "RCED_%s.ckpt" % arch)
+            os.makedirs(os.path.dirname(prefix))
+            w = network.random_weights(arch, seed=case.WEIGHT_SEED, randomize_bn=True)
+            np.savez(prefix + ".standin.npz", **w)
+            cfg, items = case.build(d, arch, prefix)
+            ref_import.WRITTEN.clear()
+            tf_standin.reset_graph()               # a fresh default graph per model, as a fresh process would have
+            printed = io.StringIO()
+            with contextlib.redirect_stdout(printed):
+                entry.main(load_conf(cfg), 1)
+            t = Recording.last
+            for i, (pc, pm, L) in enumerate(items):
+                de, rate = ref_import.WRITTEN[os.path.join(d, "out", "utt%d_de.wav" % i)]
+                assert rate == 8000 and len(de) == L
+                out["de_%s_%d" % (arch, i)] = np.asarray(de, np.float32)
+                mix, _ = ref_import.WRITTEN[os.path.join(d, "out", "utt%d_mix.wav" % i)]
+                out["mixsum_%s_%d" % (arch, i)] = np.array([float(np.abs(mix.astype(np.float64)).sum())])
+            # infer.py: InferenceEngine(cfg).denoise(file) on the second noisy file (its reshape of the [F, T] arrays included)
+            ref_import.WRITTEN.clear()
+            tf_standin.reset_graph()
+            with contextlib.redirect_stdout(printed):
+                entry.infer.InferenceEngine(load_conf(cfg)).denoise(items[1][1])
+            (path, (de, rate)), = ref_import.WRITTEN.items()
+            assert path == os.path.join(d, "out", "utt1_noisy_de.wav") and rate == 8000 and len(de) == items[1][2]
+            out["infer_de_" + arch] = np.asarray(de, np.float32)
+            out["sdr_avg_" + arch] = np.array([t.sdr_score.avg])
+            out["stoi_avg_" + arch] = np.array([t.stoi_score.avg])
+            total = [ln for ln in printed.getvalue().splitlines() if ln.startswith("Total number of Parameters")][0]
+            out["param_total_" + arch] = np.array([int(total.split(":")[1])])
+            print(arch, "SDR %.4f STOI %.4f" % (t.sdr_score.avg, t.stoi_score.avg), total)
+    np.savez_compressed(os.path.join(HERE, "reference_test_entry.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "reference_test_entry":
+        make_reference_test_entry()
+        print("reference_test_entry.npz", os.path.getsize(os.path.join(HERE, "reference_test_entry.npz")))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "network_ref_model":
         make_network_ref_model()
         print("network_ref_model.npz", os.path.getsize(os.path.join(HERE, "network_ref_model.npz")))
@@ -118,6 +183,7 @@ def main():
             net["y_%s_%d" % (arch, T)] = network.forward(arch, w, x, np.float64)
     np.savez_compressed(os.path.join(HERE, "network_oracle.npz"), **net)
     make_network_ref_model()
+    make_reference_test_entry()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
