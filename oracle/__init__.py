@@ -16,8 +16,8 @@ Parity pinning status:
 * ``oracle.network`` restates TensorFlow-1.14 graph semantics
   (``model_utils/module.py:11-34``, ``model_utils/model.py:6-96``).  TensorFlow
   1.14 (``requriements.txt:4``) is not installable here and the reference ships no
-  tests, checkpoints or golden vectors, so this part is **parity unpinned**: it is
-  anchored only on (a) the published parameter counts 32,765 / 32,192 / 32,653
+  tests, checkpoints or golden vectors, so the arithmetic of TensorFlow's operations
+  is **parity unpinned**: it is anchored on (a) the published parameter counts 32,765 / 32,192 / 32,653
   (``readme.md:63-67``), (b) agreement between two independently written
   evaluators (a tap-loop NHWC SAME convolution in numpy float64 and
   ``torch.nn.functional.conv2d`` with explicit asymmetric padding), and (c) the
@@ -28,5 +28,8 @@ Parity pinning status:
   restatement (``tests/golden/network_ref_model.npz``, agreement 2e-15).  What stays
   unpinned is the arithmetic of the three TensorFlow operations themselves (SAME
   padding of the even time kernel, batch-norm epsilon), stated from TensorFlow's
-  documented behaviour in four independently written forms.
+  documented behaviour in four independently written forms.  The same stand-in in graph
+  mode runs the reference's ENTRY POINTS unmodified (``test.py main()``,
+  ``infer.py InferenceEngine.denoise``; ``oracle/ref_import.load_test_entry``):
+  ``tests/golden/reference_test_entry.npz``, ``tests/test_reference_entry.py``.
 """

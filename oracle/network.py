@@ -1,4 +1,5 @@
-"""CPU restatement of the reference network graph (test oracle; PARITY UNPINNED).
+"""CPU restatement of the reference network graph (test oracle; wiring pinned against the reference's executed model
+code, the arithmetic of TensorFlow's three operations PARITY UNPINNED).
 
 Restates /root/reference/model_utils/module.py:11-34 (conv_bn_relu) and
 /root/reference/model_utils/model.py:6-96 (R-CED V1/V2, CR-CED V3) with the
