@@ -266,11 +266,11 @@ def roofline_tc(achieved, ffma_peak, flops_valid, k2_ms, share, rows, tc_status,
 
 
 def roofline_ffma(achieved, ffma_peak, flops_valid, k2_ms):
-    ncu = ncu_figures("k2_dram_traffic.json", ["rced_net.cu"])
+    ncu = ncu_figures("r02_k2ffma_ncu.json", ["rced_net.cu", "rced_arch.cuh"])
     return {"bound": "fp32_ffma", "kernel": "rced_net_kernel<2,TMEM> (fused 16-layer network, FP32 FFMA2)", "achieved": achieved,
             "peak": ffma_peak, "unit": "TFLOP/s", "frac": achieved / ffma_peak, "kernel_ms": k2_ms,
             "flops_per_launch": flops_valid, "flop_basis": "valid-tap MACs x2 (3,959,092 MAC/frame)",
-            "traffic": ncu.get("dram_bytes_per_launch") if ncu else None,
+            "traffic": ncu.get("dram_bytes_per_launch") if ncu else None, "ncu": ncu,
             "peak_source": "measured in this run by rced_ffma_peak (independent FFMA chains, 64 warps/SM); "
                            "MEASURED_PEAKS.json holds no FP32 figure; nominal 2*128*148*1.965 GHz = 74.4"}
 
