@@ -472,10 +472,13 @@ int rced_set_variant(rced_handle* h, int variant) {
         h->d_tc_skip = d_skip;
         h->d_tc_busy = d_busy;
         h->d_tc_flags = d_flags;
-        // Optional (RCED_TC_L2_PERSIST=1, measured in DESIGN.md): set aside L2 for persisting lines and mark the
-        // scratch with an access-policy window on every launch.
+        // L2 set aside for persisting lines (cudaLimitPersistingL2CacheSize, a device-wide limit) and an access-policy
+        // window over the scratch on every launch.  Alone the kernel does not care (13.33 against 13.32 ms: the scratch's
+        // reads hit the L2 anyway), but the host pipeline's H2D copies are written through the L2 and push the scratch out
+        // of it: with the window 13.75 instead of 14.22 ms per step end to end.  RCED_TC_L2_PERSIST=0
+        // switches it off.
         const char* pers = getenv("RCED_TC_L2_PERSIST");
-        if (pers && atoi(pers) > 0) {
+        if (!pers || atoi(pers) > 0) {
             cudaDeviceProp prop;
             if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
                 size_t want = skip_bytes;

@@ -256,7 +256,11 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
 
     // ---- copy-in: behind the kernels that read this set's previous waveforms and tables
     // development aid (tools/e2e_sweep.py): RCED_HOST_NOCOPY=1 leaves the waveform copies out to see what they cost
-    static const bool no_copy = getenv("RCED_HOST_NOCOPY") != nullptr;
+    // ("in" / "out": only that direction is left out)
+    static const char* no_copy_env = getenv("RCED_HOST_NOCOPY");
+    static const bool no_copy_in = no_copy_env && strcmp(no_copy_env, "out") != 0;
+    static const bool no_copy_out = no_copy_env && strcmp(no_copy_env, "in") != 0;
+    const bool no_copy = no_copy_in;
     const bool relay = pipe->relay >= 0 && !pipe->recomputing && !inline_copies && !compact_in && !compact_out;
     const size_t in_bytes = (size_t)(in_hi - in_lo) * sizeof(float), out_bytes = (size_t)(o_hi - o_lo) * sizeof(float);
     cudaStreamWaitEvent(s_in, b.computed, 0);
@@ -324,7 +328,7 @@ static int run_chunk(rced_handle* h, HostPipe* pipe, BufferSet& b, const float* 
         pipe->pending.push_back(PendingChunk{wav, wav_off, wav_len, c0, c1, irfft_n, out, out_off, out_len});
     }
     e = cudaSuccess;
-    if (no_copy) {
+    if (no_copy_out) {
     } else if (out_contiguous && relay) {
         // this device -> relay device (NVLink) -> host, on the relay's copy-out stream
         cudaSetDevice(pipe->relay);

@@ -115,7 +115,11 @@ int rced_set_skip_in_tmem(rced_handle* h, int enable);
  *     accuracy.  What remains is growth INSIDE the network: the kernel records the largest
  *     |activation| it stored (scaled domain, limit 65504: 4000 x the frame's reference magnitude) and
  *     whether an input was not finite, and, stream-ordered, the FFMA kernel recomputes the call when
- *     that guard tripped.  Refused (RCED_ERR_STATE) only if a folded weight is not finite. */
+ *     that guard tripped.  Refused (RCED_ERR_STATE) only if a folded weight is not finite.
+ *     Side effect on the device: the first switch to RCED_VARIANT_TC sets cudaLimitPersistingL2CacheSize (a device-wide
+ *     limit) to hold the kernel's skip scratch, and its launches carry an access-policy window over that scratch, so that
+ *     other kernels and the host copies do not push it out of the L2; RCED_TC_L2_PERSIST=0 in the environment leaves the
+ *     limit alone. */
 int rced_set_variant(rced_handle* h, int variant);
 int rced_variant(const rced_handle* h);
 /* Largest |activation| stored by the last tensor-core launch (in the frames' scaled domains; infinity:
